@@ -1,0 +1,94 @@
+"""Pins oracle/nrmp.py + oracle/ipm.py: the two independently written float64 solvers agree, the
+solver-free KKT certificate holds, and the reference-made golden vectors for the pieces that *can*
+run here (kinematics linearisation, stop criterion) are reproduced bit-for-bit."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import CONFIGS, GOLDEN, make_inputs, oracle_factory, robot_spec, weights_path
+from oracle import dune as od, ipm as oi, nrmp as onr, pan as op
+
+
+def _problems(cname, n):
+    cfg = CONFIGS[cname]
+    rb, spec = robot_spec(cfg)
+    w = od.load_weights(weights_path(cfg.model))
+    G = torch.from_numpy(rb.G).float(); h = torch.from_numpy(rb.h).float()
+    inp = make_inputs(cfg, B=n, N=min(cfg.N, 200))
+    for b in range(n):
+        vel = None if inp["velocities"] is None else torch.from_numpy(inp["velocities"][b])
+        p0, R, pl = od.point_flow(torch.from_numpy(inp["nom_s"][b]), torch.from_numpy(inp["points"][b]), vel, cfg.T, cfg.dt, 10 ** 6)
+        mu, lam, sp, _, _ = od.dune_forward(w, G, h, p0, R, pl)
+        fa, fb = od.nrmp_coefficients(h, mu, lam, sp, cfg.T, cfg.M)
+        yield onr.build_problem(spec, onr.Adjust(**cfg.adjust), inp["nom_s"][b], inp["nom_u"][b], inp["ref_s"][b], inp["ref_us"][b],
+                                fa.numpy(), fb.numpy(), cfg.M)
+
+
+@pytest.mark.parametrize("cname", ["C1", "C2", "C3", "C4", "C5"])
+def test_ipm_is_kkt_optimal_and_highs_agrees(cname):
+    worst_h = 0.0
+    for prob in _problems(cname, 4):
+        S, U, D, it = oi.solve_ipm(prob)
+        res, viol = onr.kkt_certificate(prob, S, U, D)
+        assert res < 1e-7 and viol < 1e-9, (res, viol)  # certified optimum of the convex program
+        S1, U1, D1, ok = onr.solve_highs(prob)
+        assert ok
+        o_i, o_h = onr.objective(prob, S, U, D[0]), onr.objective(prob, S1, U1, D1[0])
+        assert abs(o_i - o_h) < 1e-4 * max(1.0, abs(o_i))
+        worst_h = max(worst_h, np.abs(U - U1).max(), np.abs(S - S1).max(), np.abs(D - D1).max())
+    assert worst_h < 5e-3  # HiGHS' active-set QP stops at ~1e-6 typical, 1e-3 worst (its KKT residual is larger)
+
+
+def test_no_obs_and_vector_qs():
+    cfg = CONFIGS["C4"]
+    rb, spec = robot_spec(cfg)
+    inp = make_inputs(cfg, B=2, N=8)
+    for q_s in (0.7, [0.5, 0.6, 0.1]):
+        prob = onr.build_problem(spec, onr.Adjust(q_s=q_s), inp["nom_s"][0], inp["nom_u"][0], inp["ref_s"][0], inp["ref_us"][0], None, None, 0)
+        S, U, D, _ = oi.solve_ipm(prob)
+        assert D is None
+        res, viol = onr.kkt_certificate(prob, S, U, None)
+        assert res < 1e-7 and viol < 1e-9
+        S1, U1, _, ok = onr.solve_highs(prob)
+        assert ok and np.abs(U - U1).max() < 1e-3
+
+
+@pytest.mark.parametrize("kin", ["diff", "acker", "omni"])
+def test_linearise_matches_reference_golden(kin):
+    z = np.load(f"{GOLDEN}/ref_misc.npz")
+    A, B, C = onr.linearise(kin, z[f"lin_{kin}_nom_s"], z[f"lin_{kin}_nom_u"], 0.1, 3 if kin == "acker" else None)
+    assert np.array_equal(A, z[f"lin_{kin}_A"])
+    assert np.array_equal(B, z[f"lin_{kin}_B"])
+    assert np.array_equal(C[:, :, None], z[f"lin_{kin}_C"])
+
+
+def test_stop_criterion_matches_reference_golden():
+    z = np.load(f"{GOLDEN}/ref_misc.npz")
+    pan = types.SimpleNamespace(current=[None] * 4, nrmp_max_num=10, iter_threshold=0.1)
+    for it in range(3):
+        mu = [torch.from_numpy(m) for m in z[f"stop_{it}_mu"]]; lam = [torch.from_numpy(m) for m in z[f"stop_{it}_lam"]]
+        flag = op.OraclePAN._stop(pan, torch.zeros(3, 11), torch.zeros(2, 10), mu, lam)
+        assert flag == bool(z[f"stop_{it}_flag"])
+        if it > 0:
+            assert np.float32(pan.last_diff) == z[f"stop_{it}_diff"]
+
+
+@pytest.mark.parametrize("cname", ["C1", "C2", "C4", "C5"])
+@pytest.mark.parametrize("scene", ["annulus", "obstacles"])
+def test_oracle_pan_trace_regression(cname, scene):
+    """The committed per-iteration oracle traces are reproduced one iteration at a time (teacher
+    forced), which is robust to 1-ulp differences between CPUs; guards the oracle itself."""
+    cfg = CONFIGS[cname]
+    z = np.load(f"{GOLDEN}/oracle_pan_{cname}_{scene}.npz")
+    inp = make_inputs(cfg, B=1, scene=scene)
+    mk = oracle_factory(cfg, K=1)
+    vel = None if inp["velocities"] is None else inp["velocities"][0]
+    s, u = inp["nom_s"][0], inp["nom_u"][0]
+    for k in range(min(int(z["K"]), 3)):
+        pan = mk()
+        S, U, D = pan.forward(s, u, inp["ref_s"][0], inp["ref_us"][0], inp["points"][0], vel)
+        assert np.abs(S - z["S"][0, k]).max() < 2e-5 and np.abs(U - z["U"][0, k]).max() < 2e-5
+        assert np.abs(D - z["D"][0, k]).max() < 2e-5 and abs(pan.min_distance - z["min_distance"][0, k]) < 1e-6
+        s, u = z["S"][0, k], z["U"][0, k]
