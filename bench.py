@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- PAN control steps/sec on the BASELINE.json north-star workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C4]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one batched PAN.forward (iter_num fixed at the config's K by iter_threshold = 0) over
+B environments per GPU (weak scaling: every rank owns B envs of the same seeded family, env ids
+offset by rank*B; at the end of each step the per-env trajectories are gathered with one NCCL
+all_gather, inside the timed region).  Prints ONE JSON line (rank 0).
+
+  value ...... env-steps/s, inputs resident in HBM, device-timed (CUDA events, max over ranks)
+  e2e ........ same metric through the public API with pinned HOST tensors (H2D + D2H inside)
+  roofline ... DUNE kernel (the dominant launch): algorithmic GEMM FLOPs / CUDA-event duration
+  cpu_baseline the CPU oracle (port of the reference path) on the box's host cores, bounded sample
+
+--impl reference times that CPU path alone, on all host cores (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "PAN control steps/sec (batched envs, T x N x K)"
+UNIT = "env-steps/s"
+F_PT = 8576  # GEMM FLOPs per point-step at E=4: 2*(2*32 + 4*32*32 + 32*4)   
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        z = json.load(open(path))
+        return dict(hbm_gbs=z["hbm_gbs"], tflops=z["bf16_tflops_sustained"], which="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, which="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------
+# CPU path (the oracle port of the reference: oracle/pan.py) -- cpu_baseline and --impl reference
+# --------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    cname, env_ids, K = args
+    import torch
+
+    torch.set_num_threads(1)
+    from helpers import CONFIGS, make_inputs, oracle_factory
+
+    cfg = CONFIGS[cname]
+    mk = oracle_factory(cfg, K=K)
+    t0 = time.perf_counter()
+    for e in env_ids:
+        inp = make_inputs(cfg, B=1, env_offset=e)
+        pan = mk()
+        vel = None if inp["velocities"] is None else inp["velocities"][0]
+        pan.forward(inp["nom_s"][0], inp["nom_u"][0], inp["ref_s"][0], inp["ref_us"][0], inp["points"][0], vel)
+    return time.perf_counter() - t0
+
+
+def cpu_path_rate(cname: str, n_envs: int, K: int, procs: int):
+    """env-steps/s of the CPU oracle using `procs` worker processes (1 torch thread each)."""
+    import multiprocessing as mp
+
+    chunks = [list(range(i, n_envs, procs)) for i in range(procs)]
+    chunks = [c for c in chunks if c]
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(len(chunks)) as pool:
+        pool.map(_cpu_worker, [(cname, c, K) for c in chunks])
+    wall = time.perf_counter() - t0
+    return n_envs / wall, wall
+
+
+def run_reference(args):
+    from helpers import CONFIGS
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CONFIGS[args.workload]
+    cores = os.cpu_count() or 1
+    per_step = max(cores, min(4 * cores, 64))
+    cpu_path_rate(args.workload, cores, cfg.K, cores)  # warm-up: imports, page-in
+    times = []
+    for _ in range(max(1, min(args.steps, 3))):
+        rate, wall = cpu_path_rate(args.workload, per_step, cfg.K, cores)
+        times.append(wall)
+    ms = 1e3 * float(np.mean(times))
+    value = per_step / (ms / 1e3)
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=len(times), warmup=1, ms_per_step=ms, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32 (MLP) / f64 (QP)", data="synthetic", impl="reference",
+                config=dict(workload=f"{args.workload} {cfg.name}: T={cfg.T} N={cfg.N} K={cfg.K} M={cfg.M}", envs_per_step=per_step),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{per_step} envs/step x {len(times)} steps of {args.workload}, oracle/pan.py (reference DUNE code restated + float64 IPM for the ECOS solve; cvxpylayers/ECOS not installable)"),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from gpu_helpers import make_pan
+    from helpers import CONFIGS, make_inputs
+    from neupan_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = CONFIGS[args.workload]
+    B = args.envs or cfg.B
+    T, N, K = cfg.T, cfg.N, cfg.K
+
+    # rotating input sets (distinct envs) so consecutive steps never see the same data; plus an L2 flush
+    n_sets = 2
+    sets = []
+    for s in range(n_sets):
+        inp = make_inputs(cfg, B=B, env_offset=(rank * n_sets + s) * B)
+        sets.append({k: (None if v is None else torch.from_numpy(v)) for k, v in inp.items()})
+    dsets = [{k: (None if v is None else v.to(dev)) for k, v in s.items()} for s in sets]
+    hsets = [{k: (None if v is None else v.pin_memory()) for k, v in s.items()} for s in sets]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    pan = make_pan(cfg, K=K, iter_threshold=0.0, max_envs=B)
+    lib = _lib.load()
+    per_env = 3 * (T + 1) + 2 * T + T + 1
+    packed = torch.empty(B, per_env, device=dev)
+    gathered = torch.empty(world * B, per_env, device=dev) if world > 1 else None
+
+    def step(i, host=False):
+        d = (hsets if host else dsets)[i % n_sets]
+        S, U, D = pan(d["nom_s"], d["nom_u"], d["ref_s"], d["ref_us"], d["points"], d["velocities"])
+        if host:
+            return S
+        if world > 1:  # the one exchange of the path: gather per-env trajectories
+            torch.cat([S.reshape(B, -1), U.reshape(B, -1), D.reshape(B, -1), pan.min_distance.reshape(B, 1)], 1, out=packed)
+            dist.all_gather_into_tensor(gathered, packed)
+        return S
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        flush.zero_()
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.nb_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush, outside the per-step events
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+    barrier()
+    launches = (lib.nb_launch_count() - l0) // max(1, args.steps)
+    step_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
+    ms = float(step_ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    status_bad = int((pan.status != 0).sum().item())
+
+    # ---- e2e: host tensors through the public API (H2D + compute + D2H per step) ----------------
+    for i in range(2):
+        step(i, host=True)
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(2, min(args.steps, 5))
+    for i in range(n_e2e):
+        step(i, host=True)
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    h2d = 4 * B * (2 * 3 * (T + 1) + 2 * T + T + (2 * N) * (2 if cfg.dynamic else 1))
+    d2h = 4 * B * (3 * (T + 1) + 2 * T + T + 1) + 8 * B
+
+    # ---- roofline of the dominant kernel (DUNE), CUDA events around back-to-back launches ----------
+    roof = None
+    if rank == 0:
+        import ctypes as C
+
+        d = dsets[0]
+        p = lambda x: None if x is None else C.c_void_p(x.data_ptr())
+        md = torch.empty(B, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        reps = 5
+        for _ in range(2):
+            _lib.check(lib.nb_dune_forward(pan._handle, B, N, p(d["nom_s"]), p(d["points"]), p(d["velocities"]), None, p(md), st))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for r in range(reps):
+            flush.zero_()
+            a.record()
+            _lib.check(lib.nb_dune_forward(pan._handle, B, N, p(d["nom_s"]), p(d["points"]), p(d["velocities"]), None, p(md), st))
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        dune_ms = tot / reps
+        flops = float(F_PT) * B * (T + 1) * N
+        pk = peaks()
+        ach = flops / (dune_ms * 1e-3) / 1e12
+        alg_bytes = 4.0 * B * ((2 * N) * (2 if cfg.dynamic else 1) + 3 * (T + 1)) + 4.0 * B * (T + 1) * cfg.M * 9
+        roof = dict(bound="tensor", achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"], traffic=None,
+                    kernel="dune_kernel<E=4,P=2,256> (FP32 FFMA pipe; no tensor-core path yet)", kernel_ms=dune_ms,
+                    share_of_step=K * dune_ms / ms, peak_source=pk["which"],
+                    fp32_ffma_nominal_tflops=148 * 128 * 2 * 1.965e-3, frac_of_fp32_nominal=ach / (148 * 128 * 2 * 1.965e-3),
+                    algorithmic_bytes_per_launch=alg_bytes, hbm_gbs_if_bytes_only=alg_bytes / (dune_ms * 1e-3) / 1e9, hbm_peak_gbs=pk["hbm_gbs"])
+
+    # ---- cpu baseline (rank 0, N = 1 only), bounded sample ------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n = max(cores, min(2 * cores, 32))
+        rate, wall = cpu_path_rate(args.workload, n, K, cores)
+        cpu = dict(value=rate, unit=UNIT, cores=cores, kind="port",
+                   sample=f"{n} envs of {args.workload} (K={K}) over {cores} processes, {wall:.1f} s wall; oracle/pan.py")
+
+    if rank == 0:
+        value = world * B / (ms * 1e-3)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 (ObsPointNet, FFMA) / f64 (NRMP interior point)",
+                    data="synthetic",
+                    config=dict(workload=f"{args.workload} {cfg.name}: B={B}/GPU T={T} N={N} K={K} M={cfg.M} dyn={cfg.dynamic}", global_batch=world * B,
+                                parallelism=f"env-sharded x{world}, one all_gather of {per_env} floats/env per step",
+                                l2="2 rotating input sets + 256 MiB flush between timed steps", scene="annulus (SURVEY 8d)"),
+                    e2e=dict(value=world * B / (float(e2e_ms.item()) * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             ms_per_step=float(e2e_ms.item()), api="neupan_b200.PAN.forward on pinned host tensors -> nb_pan_forward_host"),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu, envs_with_solver_status=status_bad,
+                    control_steps_per_s=world / (ms * 1e-3))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C4")
+    ap.add_argument("--envs", type=int, default=0, help="override B per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,148 @@
+/*
+ * neupan_b200 -- C ABI of the B200-native PAN hot path (libneupan_b200.so).
+ *
+ * The reference (hanruihua/NeuPAN) has no FFI: its boundary for this path is the Python class
+ * neupan.blocks.PAN (neupan/blocks/pan.py:27-147), constructed at neupan/neupan.py:84 and called
+ * at neupan/neupan.py:129-131.  Each entry point below names the reference interface it replaces.
+ * Plain pointers and sizes only -- no torch / C++ types.  All tensors are float32, row-major,
+ * batch-leading ("B" = number of independent environments; the reference is the B == 1 case
+ * without the leading axis).  Unless a function says "host", every data pointer is a DEVICE
+ * pointer on the handle's device, and work is enqueued on `stream` (a cudaStream_t passed as
+ * void*; NULL = the legacy default stream) without synchronising.
+ *
+ * Return value: 0 on success, a negative NB_ERR_* code otherwise; nb_last_error() gives the text
+ * (thread-local).  A per-environment solver problem never fails the call: it is reported in the
+ * `status` output instead (the reference lets solver exceptions propagate, nrmp.py:144).
+ */
+#ifndef NEUPAN_B200_H
+#define NEUPAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_VERSION 1
+
+enum { NB_KIN_DIFF = 0, NB_KIN_ACKER = 1, NB_KIN_OMNI = 2 };
+
+enum {
+  NB_OK = 0,
+  NB_ERR_INVALID = -1,   /* bad argument (ValueError / AssertionError in the reference) */
+  NB_ERR_CUDA = -2,      /* CUDA runtime error */
+  NB_ERR_CAPACITY = -3,  /* B or N above what the handle was created for */
+  NB_ERR_NO_DEVICE = -4  /* no usable CUDA device: there is NO CPU fallback */
+};
+
+/* per-environment status bits written by the NRMP solve */
+enum {
+  NB_STATUS_OK = 0,
+  NB_STATUS_MAXITER = 1,     /* interior point method hit its iteration cap */
+  NB_STATUS_NUMERIC = 2,     /* non-finite value / failed factorisation */
+  NB_STATUS_INFEASIBLE = 4   /* empty bounds (d_min > d_max, max_speed <= 0, max_acce <= 0) */
+};
+
+typedef struct nb_pan nb_pan_t; /* opaque; owns weights, workspaces and the per-env state of
+                                   PAN.current_nom_values (pan.py:100-105) */
+
+/* Everything PAN.__init__ (pan.py:43-107), NRMP.__init__ (nrmp.py:35-112) and robot.__init__
+ * (neupan/robot/robot.py:32-71) fix at construction time. */
+typedef struct {
+  int32_t receding;       /* T            pan.py:45                                  */
+  int32_t kinematics;     /* NB_KIN_*     robot.py:34,60                             */
+  int32_t edge_dim;       /* E = rows of G (3..8)   dune.py:47                       */
+  int32_t iter_num;       /* K            pan.py:48                                  */
+  int32_t nrmp_max_num;   /* M (0 => no_obs, pan.py:85)                              */
+  int32_t max_envs;       /* capacity: largest B of any later call                   */
+  int32_t max_points;     /* capacity: largest N of any later call (after decimation) */
+  int32_t device;         /* CUDA device ordinal                                     */
+  float iter_threshold;   /* pan.py:52; <= 0 never stops early                       */
+  /* Python floats in the reference (float64 constants of the convex program): */
+  double step_time;       /* dt           pan.py:46                                  */
+  double wheelbase;       /* L (acker)    robot.py:58                                */
+  double max_speed[2];    /* robot.py:61 (INFINITY allowed; acker steering is clipped to 1.57 by the caller, robot.py:63-66) */
+  double max_acce[2];     /* robot.py:62 (per second; multiplied by dt inside, robot.py:69) */
+  double ro_obs, bk;      /* nrmp.py:100-101                                         */
+  /* float32 tensors in the reference (cvxpy Parameters): */
+  float q_s[3];           /* nrmp.py:83-95 (scalar q_s => three equal entries)       */
+  float p_u, eta, d_max, d_min; /* nrmp.py:79-98                                     */
+} nb_pan_config;
+
+/* Number of float32 values of an ObsPointNet checkpoint with E outputs
+ * (obs_point_net.py:31-46): 4512 + 33*E  (4644 for E = 4). */
+int64_t nb_weight_count(int32_t edge_dim);
+
+/* Replaces PAN.__init__ -> NRMP.__init__ + DUNE.__init__/load_model (pan.py:43-107,
+ * dune.py:31-54,131-144).  `weights` (HOST) holds the state_dict tensors concatenated in key
+ * order MLP.{0,1,3,5,6,8,10,11,13}.{weight,bias}; G (E x 2) and h (E) are HOST arrays from
+ * gen_inequal_from_vertex (util/__init__.py:161-206). */
+int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weights,
+                  const float* G, const float* h, nb_pan_t** out);
+int nb_pan_destroy(nb_pan_t* pan);
+
+/* Replaces PAN.forward (pan.py:109-147): up to K iterations of {point flow -> DUNE -> NRMP ->
+ * stop criterion} for B environments.
+ *   nom_s (B,3,T+1)  nom_u (B,2,T)  ref_s (B,3,T+1)  ref_us (B,T)
+ *   points (B,2,N) or NULL (no obstacle points: pan.py:130-138 else-branch)
+ *   velocities (B,2,N) or NULL (static points, pan.py:168-169)
+ *   num_points (B) int32 or NULL: valid point count per env (ragged batches; <= N)
+ * outputs: out_s (B,3,T+1)  out_u (B,2,T)  out_d (B,T) [nom_distance, zeros in no_obs mode]
+ *   out_min_distance (B) [DUNE.min_distance, dune.py:97-98; +inf without points]
+ *   out_iters (B) int32 or NULL: iterations executed per env;  out_status (B) int32 or NULL.
+ * Inputs are never modified; outputs may not alias inputs. */
+int nb_pan_forward(nb_pan_t* pan, int32_t B, int32_t N,
+                   const float* nom_s, const float* nom_u, const float* ref_s, const float* ref_us,
+                   const float* points, const float* velocities, const int32_t* num_points,
+                   float* out_s, float* out_u, float* out_d, float* out_min_distance,
+                   int32_t* out_iters, int32_t* out_status, void* stream);
+
+/* Same call with HOST buffers (what neupan.forward does around PAN: np_to_tensor / tensor_to_np,
+ * neupan/neupan.py:123-135): stages through the handle's device workspace on `stream` and
+ * returns after the results have landed in the host buffers. */
+int nb_pan_forward_host(nb_pan_t* pan, int32_t B, int32_t N,
+                        const float* nom_s, const float* nom_u, const float* ref_s, const float* ref_us,
+                        const float* points, const float* velocities, const int32_t* num_points,
+                        float* out_s, float* out_u, float* out_d, float* out_min_distance,
+                        int32_t* out_iters, int32_t* out_status, void* stream);
+
+/* Replaces NRMP.update_adjust_parameters_value (nrmp.py:171-217). */
+int nb_pan_set_adjust(nb_pan_t* pan, const float q_s[3], float p_u, float eta, float d_max, float d_min);
+/* iter_num / iter_threshold are plain attributes in the reference (pan.py:63-64). */
+int nb_pan_set_iteration(nb_pan_t* pan, int32_t iter_num, float iter_threshold);
+
+/* Forget PAN.current_nom_values (pan.py:100-105) of all environments.  (The reference's
+ * neupan.reset() does NOT do this, neupan/neupan.py:288-294; exposed for tests and for
+ * re-using a handle on a new batch.) */
+int nb_pan_reset_state(nb_pan_t* pan);
+
+/* The sorted selections of the last executed iteration, what DUNE.forward returns restricted to
+ * the first M columns (dune.py:100-104): mu (B,T+1,M,E) lam (B,T+1,M,2) points (B,T+1,M,2)
+ * distance (B,T+1,M) count (B) int32 [= min(num_points, M)].  Any pointer may be NULL.
+ * sel_points[:,0] is NRMP.points / PAN.nrmp_points (nrmp.py:135-138, pan.py:262-268). */
+int nb_pan_read_selection(nb_pan_t* pan, int32_t B, float* sel_mu, float* sel_lam, float* sel_points,
+                          float* sel_distance, int32_t* sel_count, void* stream);
+
+/* ---- the two halves, exposed separately (parity tests, profiling) ------------------------ */
+
+/* PAN.generate_point_flow + DUNE.forward (pan.py:150-212, dune.py:58-127) for B envs, keeping the
+ * M closest points per (env, step) in ascending distance order.  Results land in the handle
+ * (read them with nb_pan_read_selection); out_min_distance (B) may be NULL. */
+int nb_dune_forward(nb_pan_t* pan, int32_t B, int32_t N, const float* nom_s, const float* points,
+                    const float* velocities, const int32_t* num_points, float* out_min_distance, void* stream);
+
+/* NRMP.forward (nrmp.py:114-150) for B envs on explicit obstacle coefficients:
+ * fa (B,T,M,2) = lam^T rows, fb (B,T,M) = lam^T p + mu^T h (nrmp.py:220-261); NULL => zeros. */
+int nb_nrmp_forward(nb_pan_t* pan, int32_t B, const float* nom_s, const float* nom_u, const float* ref_s,
+                    const float* ref_us, const float* fa, const float* fb,
+                    float* out_s, float* out_u, float* out_d, int32_t* out_status, void* stream);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t nb_launch_count(void);
+const char* nb_last_error(void);
+int nb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUPAN_B200_H */

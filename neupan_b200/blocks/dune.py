@@ -1,0 +1,59 @@
+"""DUNE layer facade (mirrors neupan/blocks/dune.py:29-216).
+
+Holds what the reference's DUNE holds -- the ObsPointNet parameters, G, h, ``min_distance``,
+``points`` -- and loads the same checkpoints.  Its per-step computation (dune.py:58-127) happens
+inside the CUDA DUNE kernel driven by PAN; this class owns no compute.
+"""
+from __future__ import annotations
+
+from math import inf
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ..util import file_check
+from .obs_point_net import ObsPointNet
+
+
+class DUNE(torch.nn.Module):
+    def __init__(self, receding: int = 10, checkpoint=None, robot=None, dune_max_num: int = 100, train_kwargs: Optional[dict] = None) -> None:
+        super().__init__()
+        if robot is None:
+            raise ValueError("robot parameter is required and cannot be None")  # dune.py:37-38
+        self.T = receding
+        self.max_num = dune_max_num
+        self.robot = robot
+        self.G = torch.from_numpy(np.asarray(robot.G)).float()
+        self.h = torch.from_numpy(np.asarray(robot.h)).float()
+        self.edge_dim = self.G.shape[0]
+        self.state_dim = self.G.shape[1]
+        self.model = ObsPointNet(2, self.edge_dim)
+        self.load_model(checkpoint, train_kwargs)
+        self.obstacle_points = None
+        self.min_distance = inf
+
+    def load_model(self, checkpoint: Optional[str] = None, train_kwargs: Optional[dict] = None):
+        """dune.py:131-170 without the interactive prompts: a missing checkpoint raises
+        FileNotFoundError unless ``train_kwargs['direct_train']`` is set (weights stay at init)."""
+        if checkpoint is None or str(checkpoint) == "None":
+            if train_kwargs and train_kwargs.get("direct_train", False):
+                return
+            raise FileNotFoundError("DUNE checkpoint is required (pan.dune_checkpoint); training on demand is not part of the hot path")
+        if str(checkpoint).endswith(".npz"):
+            path = file_check(checkpoint)
+            z = np.load(path)
+            sd = {k: torch.from_numpy(z[k]) for k in z.files if k.startswith("MLP.")}
+        else:
+            path = file_check(checkpoint)
+            sd = torch.load(path, map_location=torch.device("cpu"))
+        self.abs_checkpoint_path = path
+        self.model.load_state_dict(sd)
+        self.model.eval()
+
+    def train_dune(self, train_kwargs):
+        raise NotImplementedError("DUNE training (neupan/blocks/dune_train.py) is outside the B200 hot path (SURVEY.md 8f #4)")
+
+    @property
+    def points(self):
+        return self.obstacle_points

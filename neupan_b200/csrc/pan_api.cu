@@ -1,0 +1,409 @@
+// C-ABI of the PAN hot path (include/neupan_b200.h): handle, workspaces, launch logic.
+// No torch, no C++ types across the boundary.  One handle = one (process, GPU); not thread-safe.
+#include "../../include/neupan_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "dune_launch.cuh"
+#include "nrmp_kernel.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+long long g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define NB_CUDA(call)                                                                             \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) return fail(NB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t n) {
+  return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
+}
+
+}  // namespace
+
+struct nb_pan {
+  nb_pan_config cfg;
+  nb::Geometry geo;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  // device buffers
+  float* d_weights = nullptr;
+  float *sel_mu = nullptr, *sel_lam = nullptr, *sel_pts = nullptr, *sel_dist = nullptr;
+  int32_t* sel_count = nullptr;
+  float *prev_s = nullptr, *prev_u = nullptr, *prev_mu = nullptr, *prev_lam = nullptr;
+  int32_t *prev_count = nullptr, *prev_valid = nullptr, *active = nullptr, *iters = nullptr, *status = nullptr;
+  float* min_dist = nullptr;
+  // staging for the host-pointer entry point
+  float *h_in = nullptr, *h_out = nullptr;  // device staging
+  size_t h_in_floats = 0, h_out_floats = 0;
+  int32_t* h_np = nullptr;
+  int32_t* h_io = nullptr;
+  bool dune_attr_set = false, nrmp_attr_set = false;
+};
+
+namespace {
+
+int check_forward_args(const nb_pan* p, int B, int N) {
+  if (!p) return fail(NB_ERR_INVALID, "null handle");
+  if (B <= 0) return fail(NB_ERR_INVALID, "B must be positive (got %d)", B);
+  if (B > p->cfg.max_envs) return fail(NB_ERR_CAPACITY, "B=%d exceeds max_envs=%d", B, p->cfg.max_envs);
+  if (N < 0) return fail(NB_ERR_INVALID, "N must be >= 0");
+  if (N > p->cfg.max_points) return fail(NB_ERR_CAPACITY, "N=%d exceeds max_points=%d", N, p->cfg.max_points);
+  return NB_OK;
+}
+
+// NB_EDGE_MASK: bit E set <=> dune_inst.cu was compiled for that edge count (build script)
+#ifndef NB_EDGE_MASK
+#define NB_EDGE_MASK 0x10
+#endif
+
+int launch_dune(nb_pan* p, const nb::DuneParams& prm, cudaStream_t st) {
+  int rc = NB_ERR_INVALID;
+  char msg[256] = "";
+  switch (p->cfg.edge_dim) {
+#define NB_CASE(E_)                                                                                        \
+  case E_:                                                                                                 \
+    rc = nb::launch_dune_e<E_>(prm, p->sm_count, p->max_smem_optin, st, msg, sizeof(msg));                 \
+    break;
+#if NB_EDGE_MASK & (1 << 3)
+    NB_CASE(3)
+#endif
+#if NB_EDGE_MASK & (1 << 4)
+    NB_CASE(4)
+#endif
+#if NB_EDGE_MASK & (1 << 5)
+    NB_CASE(5)
+#endif
+#if NB_EDGE_MASK & (1 << 6)
+    NB_CASE(6)
+#endif
+#if NB_EDGE_MASK & (1 << 7)
+    NB_CASE(7)
+#endif
+#if NB_EDGE_MASK & (1 << 8)
+    NB_CASE(8)
+#endif
+#undef NB_CASE
+    default:
+      return fail(NB_ERR_INVALID, "edge_dim %d not built into this library (mask 0x%x)", p->cfg.edge_dim, NB_EDGE_MASK);
+  }
+  if (rc) return fail(rc, "%s", msg);
+  ++g_launches;
+  return NB_OK;
+}
+
+int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st) {
+  const nb_pan_config& c = p->cfg;
+  prm.T = c.receding; prm.M = c.nrmp_max_num; prm.E = c.edge_dim; prm.kin = c.kinematics;
+  prm.max_ipm_iter = 60;
+  prm.iter_threshold = c.iter_threshold;
+  prm.dt = c.step_time; prm.L = c.wheelbase;
+  for (int i = 0; i < 3; ++i) prm.q[i] = c.q_s[i];
+  prm.p_u = c.p_u; prm.eta = c.eta; prm.d_max = c.d_max; prm.d_min = c.d_min;
+  prm.ro = c.ro_obs; prm.bk = c.bk;
+  for (int i = 0; i < 2; ++i) {
+    prm.speed[i] = c.max_speed[i];
+    prm.acce[i] = c.max_acce[i] * c.step_time;
+  }
+  for (int e = 0; e < nb::kMaxEdges; ++e) prm.h[e] = p->geo.h[e];
+  const size_t wd = nb::nrmp_warp_doubles(prm.T, prm.M);
+  int warps = (int)((size_t)p->max_smem_optin / (wd * sizeof(double)));
+  if (warps < 1) return fail(NB_ERR_CAPACITY, "T=%d, M=%d need %zu B of shared memory per environment", prm.T, prm.M, wd * 8);
+  // two CTAs per SM when possible so that one CTA's tail overlaps the other's work
+  if (warps >= 4) warps = warps / 2;
+  if (warps > 8) warps = 8;
+  const size_t smem = (size_t)warps * wd * sizeof(double);
+  if (!p->nrmp_attr_set) {
+    NB_CUDA(cudaFuncSetAttribute(nb::nrmp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem_optin));
+    p->nrmp_attr_set = true;
+  }
+  const int grid = (prm.B + warps - 1) / warps;
+  nb::nrmp_kernel<<<grid, warps * 32, smem, st>>>(prm, warps, (int)wd);
+  ++g_launches;
+  NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+
+__global__ void init_run_kernel(int B, int32_t* active, int32_t* iters, int32_t* status, float* min_dist, int32_t* sel_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    active[i] = 1; iters[i] = 0; status[i] = 0;
+    min_dist[i] = __int_as_float(0x7f800000);
+    sel_count[i] = 0;
+  }
+}
+
+__global__ void finish_run_kernel(int B, const int32_t* iters, const int32_t* status, const float* min_dist,
+                                  int32_t* out_iters, int32_t* out_status, float* out_min_dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    if (out_iters) out_iters[i] = iters[i];
+    if (out_status) out_status[i] = status[i];
+    if (out_min_dist) out_min_dist[i] = min_dist[i];
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t nb_weight_count(int32_t edge_dim) { return nb::WeightLayout::count(edge_dim); }
+int nb_version(void) { return NB_VERSION; }
+const char* nb_last_error(void) { return g_err; }
+int64_t nb_launch_count(void) { return g_launches; }
+
+int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weights, const float* G, const float* h, nb_pan_t** out) {
+  if (!cfg || !out) return fail(NB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->receding < 1 || cfg->receding > 32) return fail(NB_ERR_INVALID, "receding must be in 1..32 (got %d)", cfg->receding);
+  if (cfg->kinematics < 0 || cfg->kinematics > 2) return fail(NB_ERR_INVALID, "kinematics must be NB_KIN_DIFF/ACKER/OMNI");
+  if (cfg->nrmp_max_num < 0 || cfg->nrmp_max_num > 64) return fail(NB_ERR_INVALID, "nrmp_max_num must be in 0..64");
+  if (cfg->iter_num < 0) return fail(NB_ERR_INVALID, "iter_num must be >= 0");
+  if (cfg->max_envs < 1 || cfg->max_points < 0) return fail(NB_ERR_INVALID, "max_envs >= 1 and max_points >= 0 required");
+  if (!(cfg->step_time > 0)) return fail(NB_ERR_INVALID, "step_time must be positive");
+  if (cfg->kinematics == NB_KIN_ACKER && !(cfg->wheelbase > 0)) return fail(NB_ERR_INVALID, "acker needs a positive wheelbase");
+  const bool with_dune = cfg->nrmp_max_num > 0;
+  if (with_dune) {
+    if (cfg->edge_dim < 3 || cfg->edge_dim > nb::kMaxEdges) return fail(NB_ERR_INVALID, "edge_dim must be in 3..%d", nb::kMaxEdges);
+    if (!weights || !G || !h) return fail(NB_ERR_INVALID, "weights, G and h are required when nrmp_max_num > 0");
+    if (n_weights != nb::WeightLayout::count(cfg->edge_dim))
+      return fail(NB_ERR_INVALID, "expected %d weights for edge_dim %d, got %lld", nb::WeightLayout::count(cfg->edge_dim), cfg->edge_dim, (long long)n_weights);
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(NB_ERR_NO_DEVICE, "no CUDA device available: neupan_b200 has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(NB_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+  NB_CUDA(cudaSetDevice(cfg->device));
+  nb_pan* p = new (std::nothrow) nb_pan();
+  if (!p) return fail(NB_ERR_INVALID, "out of host memory");
+  p->cfg = *cfg;
+  NB_CUDA(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
+  NB_CUDA(cudaDeviceGetAttribute(&p->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+  memset(&p->geo, 0, sizeof(p->geo));
+  p->geo.E = cfg->edge_dim;
+  const size_t B = cfg->max_envs, T1 = cfg->receding + 1, T = cfg->receding, M = cfg->nrmp_max_num, E = with_dune ? cfg->edge_dim : 1;
+  if (with_dune) {
+    for (int e = 0; e < cfg->edge_dim; ++e) {
+      p->geo.G[e][0] = G[2 * e]; p->geo.G[e][1] = G[2 * e + 1]; p->geo.h[e] = h[e];
+    }
+    NB_CUDA(dalloc(&p->d_weights, (size_t)n_weights));
+    NB_CUDA(cudaMemcpy(p->d_weights, weights, (size_t)n_weights * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  NB_CUDA(dalloc(&p->sel_mu, B * T1 * M * E));
+  NB_CUDA(dalloc(&p->sel_lam, B * T1 * M * 2));
+  NB_CUDA(dalloc(&p->sel_pts, B * T1 * M * 2));
+  NB_CUDA(dalloc(&p->sel_dist, B * T1 * M));
+  NB_CUDA(dalloc(&p->sel_count, B));
+  NB_CUDA(dalloc(&p->prev_s, B * 3 * T1));
+  NB_CUDA(dalloc(&p->prev_u, B * 2 * T));
+  NB_CUDA(dalloc(&p->prev_mu, B * T1 * M * E));
+  NB_CUDA(dalloc(&p->prev_lam, B * T1 * M * 2));
+  NB_CUDA(dalloc(&p->prev_count, B));
+  NB_CUDA(dalloc(&p->prev_valid, B));
+  NB_CUDA(dalloc(&p->active, B));
+  NB_CUDA(dalloc(&p->iters, B));
+  NB_CUDA(dalloc(&p->status, B));
+  NB_CUDA(dalloc(&p->min_dist, B));
+  NB_CUDA(cudaMemset(p->prev_valid, 0, B * sizeof(int32_t)));
+  NB_CUDA(cudaMemset(p->prev_count, 0, B * sizeof(int32_t)));
+  NB_CUDA(cudaMemset(p->sel_count, 0, B * sizeof(int32_t)));
+  *out = p;
+  return NB_OK;
+}
+
+int nb_pan_destroy(nb_pan_t* p) {
+  if (!p) return NB_OK;
+  cudaSetDevice(p->cfg.device);
+  void* bufs[] = {p->d_weights, p->sel_mu, p->sel_lam, p->sel_pts, p->sel_dist, p->sel_count, p->prev_s, p->prev_u, p->prev_mu,
+                  p->prev_lam, p->prev_count, p->prev_valid, p->active, p->iters, p->status, p->min_dist, p->h_in, p->h_out, p->h_np, p->h_io};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  delete p;
+  return NB_OK;
+}
+
+int nb_pan_set_adjust(nb_pan_t* p, const float q_s[3], float p_u, float eta, float d_max, float d_min) {
+  if (!p || !q_s) return fail(NB_ERR_INVALID, "null argument");
+  for (int i = 0; i < 3; ++i) p->cfg.q_s[i] = q_s[i];
+  p->cfg.p_u = p_u; p->cfg.eta = eta; p->cfg.d_max = d_max; p->cfg.d_min = d_min;
+  return NB_OK;
+}
+
+int nb_pan_set_iteration(nb_pan_t* p, int32_t iter_num, float iter_threshold) {
+  if (!p || iter_num < 0) return fail(NB_ERR_INVALID, "bad argument");
+  p->cfg.iter_num = iter_num; p->cfg.iter_threshold = iter_threshold;
+  return NB_OK;
+}
+
+int nb_pan_reset_state(nb_pan_t* p) {
+  if (!p) return fail(NB_ERR_INVALID, "null handle");
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  NB_CUDA(cudaMemset(p->prev_valid, 0, (size_t)p->cfg.max_envs * sizeof(int32_t)));
+  NB_CUDA(cudaMemset(p->prev_count, 0, (size_t)p->cfg.max_envs * sizeof(int32_t)));
+  return NB_OK;
+}
+
+int nb_dune_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const float* points, const float* velocities,
+                    const int32_t* num_points, float* out_min_distance, void* stream) {
+  if (int rc = check_forward_args(p, B, N)) return rc;
+  if (p->cfg.nrmp_max_num == 0) return fail(NB_ERR_INVALID, "handle was created in no_obs mode");
+  if (!nom_s || !points) return fail(NB_ERR_INVALID, "nom_s and points are required");
+  if (N == 0) return fail(NB_ERR_INVALID, "N must be positive");
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  nb::DuneParams prm{};
+  prm.weights = p->d_weights; prm.nom_s = nom_s; prm.points = points; prm.velocities = velocities; prm.num_points = num_points;
+  prm.active = nullptr;
+  prm.sel_mu = p->sel_mu; prm.sel_lam = p->sel_lam; prm.sel_pts = p->sel_pts; prm.sel_dist = p->sel_dist; prm.sel_count = p->sel_count;
+  prm.min_dist = out_min_distance;
+  prm.B = B; prm.N = N; prm.T = p->cfg.receding; prm.M = p->cfg.nrmp_max_num; prm.dt = (float)p->cfg.step_time; prm.geo = p->geo;
+  return launch_dune(p, prm, (cudaStream_t)stream);
+}
+
+int nb_nrmp_forward(nb_pan_t* p, int32_t B, const float* nom_s, const float* nom_u, const float* ref_s, const float* ref_us,
+                    const float* fa, const float* fb, float* out_s, float* out_u, float* out_d, int32_t* out_status, void* stream) {
+  if (int rc = check_forward_args(p, B, 0)) return rc;
+  if (!nom_s || !nom_u || !ref_s || !ref_us || !out_s || !out_u || !out_d) return fail(NB_ERR_INVALID, "null tensor argument");
+  if ((fa == nullptr) != (fb == nullptr)) return fail(NB_ERR_INVALID, "fa and fb must be given together");
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  nb::NrmpParams prm{};
+  prm.nom_s = nom_s; prm.nom_u = nom_u; prm.ref_s = ref_s; prm.ref_us = ref_us; prm.fa = fa; prm.fb = fb;
+  prm.out_s = out_s; prm.out_u = out_u; prm.out_d = out_d; prm.status = out_status;
+  prm.B = B;
+  return launch_nrmp(p, prm, (cudaStream_t)stream);
+}
+
+int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const float* nom_u, const float* ref_s, const float* ref_us,
+                   const float* points, const float* velocities, const int32_t* num_points, float* out_s, float* out_u, float* out_d,
+                   float* out_min_distance, int32_t* out_iters, int32_t* out_status, void* stream) {
+  if (int rc = check_forward_args(p, B, N)) return rc;
+  if (!nom_s || !nom_u || !ref_s || !ref_us || !out_s || !out_u || !out_d) return fail(NB_ERR_INVALID, "null tensor argument");
+  if (velocities && !points) return fail(NB_ERR_INVALID, "velocities given without points");
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const nb_pan_config& c = p->cfg;
+  const int T = c.receding, T1 = T + 1;
+  const bool with_dune = c.nrmp_max_num > 0 && points != nullptr && N > 0;  // pan.py:130
+  const int tb = 128, gb = (B + tb - 1) / tb;
+  init_run_kernel<<<gb, tb, 0, st>>>(B, p->active, p->iters, p->status, p->min_dist, p->sel_count);
+  ++g_launches;
+  // the nominal trajectory lives in the output buffers and is updated in place every iteration
+  NB_CUDA(cudaMemcpyAsync(out_s, nom_s, (size_t)B * 3 * T1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  NB_CUDA(cudaMemcpyAsync(out_u, nom_u, (size_t)B * 2 * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  NB_CUDA(cudaMemsetAsync(out_d, 0, (size_t)B * T * sizeof(float), st));
+  for (int k = 0; k < c.iter_num; ++k) {
+    if (with_dune) {
+      nb::DuneParams d{};
+      d.weights = p->d_weights; d.nom_s = out_s; d.points = points; d.velocities = velocities; d.num_points = num_points;
+      d.active = p->active;
+      d.sel_mu = p->sel_mu; d.sel_lam = p->sel_lam; d.sel_pts = p->sel_pts; d.sel_dist = p->sel_dist; d.sel_count = p->sel_count;
+      d.min_dist = p->min_dist;
+      d.B = B; d.N = N; d.T = T; d.M = c.nrmp_max_num; d.dt = (float)c.step_time; d.geo = p->geo;
+      if (int rc = launch_dune(p, d, st)) return rc;
+    }
+    nb::NrmpParams n{};
+    n.nom_s = out_s; n.nom_u = out_u; n.ref_s = ref_s; n.ref_us = ref_us;
+    if (with_dune) { n.sel_mu = p->sel_mu; n.sel_lam = p->sel_lam; n.sel_pts = p->sel_pts; n.sel_count = p->sel_count; }
+    n.out_s = out_s; n.out_u = out_u; n.out_d = out_d; n.status = p->status; n.iters = p->iters; n.active = p->active;
+    n.prev_s = p->prev_s; n.prev_u = p->prev_u; n.prev_mu = p->prev_mu; n.prev_lam = p->prev_lam;
+    n.prev_count = p->prev_count; n.prev_valid = p->prev_valid;
+    n.B = B;
+    if (int rc = launch_nrmp(p, n, st)) return rc;
+  }
+  finish_run_kernel<<<gb, tb, 0, st>>>(B, p->iters, p->status, p->min_dist, out_iters, out_status, out_min_distance);
+  ++g_launches;
+  NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+
+int nb_pan_read_selection(nb_pan_t* p, int32_t B, float* sel_mu, float* sel_lam, float* sel_points, float* sel_distance,
+                          int32_t* sel_count, void* stream) {
+  if (int rc = check_forward_args(p, B, 0)) return rc;
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t T1 = p->cfg.receding + 1, M = p->cfg.nrmp_max_num, E = p->cfg.edge_dim;
+  if (sel_mu) NB_CUDA(cudaMemcpyAsync(sel_mu, p->sel_mu, (size_t)B * T1 * M * E * 4, cudaMemcpyDeviceToDevice, st));
+  if (sel_lam) NB_CUDA(cudaMemcpyAsync(sel_lam, p->sel_lam, (size_t)B * T1 * M * 2 * 4, cudaMemcpyDeviceToDevice, st));
+  if (sel_points) NB_CUDA(cudaMemcpyAsync(sel_points, p->sel_pts, (size_t)B * T1 * M * 2 * 4, cudaMemcpyDeviceToDevice, st));
+  if (sel_distance) NB_CUDA(cudaMemcpyAsync(sel_distance, p->sel_dist, (size_t)B * T1 * M * 4, cudaMemcpyDeviceToDevice, st));
+  if (sel_count) NB_CUDA(cudaMemcpyAsync(sel_count, p->sel_count, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  return NB_OK;
+}
+
+int nb_pan_forward_host(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const float* nom_u, const float* ref_s,
+                        const float* ref_us, const float* points, const float* velocities, const int32_t* num_points, float* out_s,
+                        float* out_u, float* out_d, float* out_min_distance, int32_t* out_iters, int32_t* out_status, void* stream) {
+  if (int rc = check_forward_args(p, B, N)) return rc;
+  if (!nom_s || !nom_u || !ref_s || !ref_us || !out_s || !out_u || !out_d) return fail(NB_ERR_INVALID, "null tensor argument");
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t T = p->cfg.receding, T1 = T + 1;
+  const size_t n_s = (size_t)B * 3 * T1, n_u = (size_t)B * 2 * T, n_r = (size_t)B * T, n_p = (size_t)B * 2 * N;
+  const size_t in_floats = 2 * n_s + n_u + n_r + 2 * n_p;
+  const size_t out_floats = n_s + n_u + n_r + (size_t)B;
+  if (in_floats > p->h_in_floats) {
+    if (p->h_in) cudaFree(p->h_in);
+    p->h_in = nullptr; p->h_in_floats = 0;
+    NB_CUDA(dalloc(&p->h_in, in_floats));
+    p->h_in_floats = in_floats;
+  }
+  if (out_floats > p->h_out_floats) {
+    if (p->h_out) cudaFree(p->h_out);
+    p->h_out = nullptr; p->h_out_floats = 0;
+    NB_CUDA(dalloc(&p->h_out, out_floats));
+    p->h_out_floats = out_floats;
+  }
+  if (!p->h_np) NB_CUDA(dalloc(&p->h_np, (size_t)p->cfg.max_envs));
+  if (!p->h_io) NB_CUDA(dalloc(&p->h_io, 2 * (size_t)p->cfg.max_envs));
+  float* d = p->h_in;
+  float* d_nom_s = d; d += n_s;
+  float* d_ref_s = d; d += n_s;
+  float* d_nom_u = d; d += n_u;
+  float* d_ref_us = d; d += n_r;
+  float* d_pts = d; d += n_p;
+  float* d_vel = d;
+  auto h2d = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st); };
+  NB_CUDA(h2d(d_nom_s, nom_s, n_s * 4));
+  NB_CUDA(h2d(d_ref_s, ref_s, n_s * 4));
+  NB_CUDA(h2d(d_nom_u, nom_u, n_u * 4));
+  NB_CUDA(h2d(d_ref_us, ref_us, n_r * 4));
+  if (points && N > 0) NB_CUDA(h2d(d_pts, points, n_p * 4));
+  if (velocities && N > 0) NB_CUDA(h2d(d_vel, velocities, n_p * 4));
+  if (num_points) NB_CUDA(h2d(p->h_np, num_points, (size_t)B * 4));
+  float* o = p->h_out;
+  float* o_s = o; o += n_s;
+  float* o_u = o; o += n_u;
+  float* o_d = o; o += n_r;
+  float* o_md = o;
+  int rc = nb_pan_forward(p, B, N, d_nom_s, d_nom_u, d_ref_s, d_ref_us, (points && N > 0) ? d_pts : nullptr,
+                          (velocities && N > 0) ? d_vel : nullptr, num_points ? p->h_np : nullptr, o_s, o_u, o_d, o_md, p->h_io,
+                          p->h_io + p->cfg.max_envs, st);
+  if (rc) return rc;
+  auto d2h = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st); };
+  NB_CUDA(d2h(out_s, o_s, n_s * 4));
+  NB_CUDA(d2h(out_u, o_u, n_u * 4));
+  NB_CUDA(d2h(out_d, o_d, n_r * 4));
+  if (out_min_distance) NB_CUDA(d2h(out_min_distance, o_md, (size_t)B * 4));
+  if (out_iters) NB_CUDA(d2h(out_iters, p->h_io, (size_t)B * 4));
+  if (out_status) NB_CUDA(d2h(out_status, p->h_io + p->cfg.max_envs, (size_t)B * 4));
+  NB_CUDA(cudaStreamSynchronize(st));
+  return NB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,23 @@
+"""Helpers for the -m gpu parity tests: build a product PAN for a workload config."""
+import numpy as np
+import torch
+
+from helpers import CONFIGS, weights_path
+from neupan_b200 import PAN
+
+
+def make_pan(cfg, K=None, iter_threshold=0.0, N=None, adjust=None, M=None, max_envs=1, dune_max_num=None):
+    rb = cfg.make_robot()
+    return PAN(cfg.T, cfg.dt, rb, iter_num=cfg.K if K is None else K, dune_max_num=(cfg.N if N is None else N) if dune_max_num is None else dune_max_num,
+               nrmp_max_num=cfg.M if M is None else M, dune_checkpoint=weights_path(cfg.model), iter_threshold=iter_threshold,
+               adjust_kwargs=dict(adjust or cfg.adjust), max_envs=max_envs, max_points=cfg.N if N is None else N)
+
+
+def to_cuda(inp):
+    return {k: (None if v is None else torch.from_numpy(np.ascontiguousarray(v)).cuda()) for k, v in inp.items()}
+
+
+def run_pan(pan, inp, cuda=True):
+    t = to_cuda(inp) if cuda else {k: (None if v is None else torch.from_numpy(v)) for k, v in inp.items()}
+    S, U, D = pan(t["nom_s"], t["nom_u"], t["ref_s"], t["ref_us"], t["points"], t["velocities"])
+    return S.cpu().numpy(), U.cpu().numpy(), D.cpu().numpy()[:, 0], pan.min_distance.cpu().numpy()
