@@ -111,6 +111,12 @@ int nb_pan_set_adjust(nb_pan_t* pan, const float q_s[3], float p_u, float eta, f
 /* iter_num / iter_threshold are plain attributes in the reference (pan.py:63-64). */
 int nb_pan_set_iteration(nb_pan_t* pan, int32_t iter_num, float iter_threshold);
 
+/* Implementation switches (no reference counterpart).  NB_OPT_DUNE_KERNEL: 1 (default) = tensor-core
+ * DUNE kernel (mma.sync, fp16 hi/lo split, fp32 accumulate); 0 = all-FP32 FFMA kernel, kept as the
+ * in-tree numerical reference of the same contract (needs the edge count compiled in). */
+enum { NB_OPT_DUNE_KERNEL = 1 };
+int nb_pan_set_option(nb_pan_t* pan, int32_t option, int32_t value);
+
 /* Forget PAN.current_nom_values (pan.py:100-105) of all environments.  (The reference's
  * neupan.reset() does NOT do this, neupan/neupan.py:288-294; exposed for tests and for
  * re-using a handle on a new batch.) */

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libneupan_b200.so")
 NB_KIN = {"diff": 0, "acker": 1, "omni": 2}
 NB_OK, NB_ERR_INVALID, NB_ERR_CUDA, NB_ERR_CAPACITY, NB_ERR_NO_DEVICE = 0, -1, -2, -3, -4
 STATUS_MAXITER, STATUS_NUMERIC, STATUS_INFEASIBLE = 1, 2, 4
+OPT_DUNE_KERNEL = 1
 
 
 class PanConfig(C.Structure):
@@ -41,6 +42,7 @@ SYMBOLS = {
     "nb_pan_forward_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [_FP] * 13 + [C.c_void_p]),
     "nb_pan_set_adjust": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 3), C.c_float, C.c_float, C.c_float, C.c_float]),
     "nb_pan_set_iteration": (C.c_int, [C.c_void_p, C.c_int32, C.c_float]),
+    "nb_pan_set_option": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "nb_pan_reset_state": (C.c_int, [C.c_void_p]),
     "nb_pan_read_selection": (C.c_int, [C.c_void_p, C.c_int32] + [_FP] * 5 + [C.c_void_p]),
     "nb_dune_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [_FP] * 5 + [C.c_void_p]),

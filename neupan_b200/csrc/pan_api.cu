@@ -12,6 +12,14 @@
 #include "dune_launch.cuh"
 #include "nrmp_kernel.cuh"
 
+#include <vector>
+
+namespace nb {
+// dune_mma.cu
+void build_mma_image(const float* w, int E, std::vector<unsigned char>& out);
+int launch_dune_mma(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, cudaStream_t st, char* err, size_t errlen);
+}  // namespace nb
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -45,6 +53,8 @@ struct nb_pan {
   int max_smem_optin = 0;
   // device buffers
   float* d_weights = nullptr;
+  unsigned char* d_image = nullptr;  // fragment-ordered fp16 hi/lo weight image of the tensor-core DUNE kernel
+  int dune_variant = 1;              // NB_OPT_DUNE_KERNEL: 0 = FP32 FFMA kernel, 1 = tensor-core kernel
   float *sel_mu = nullptr, *sel_lam = nullptr, *sel_pts = nullptr, *sel_dist = nullptr;
   int32_t* sel_count = nullptr;
   float *prev_s = nullptr, *prev_u = nullptr, *prev_mu = nullptr, *prev_lam = nullptr;
@@ -77,6 +87,12 @@ int check_forward_args(const nb_pan* p, int B, int N) {
 int launch_dune(nb_pan* p, const nb::DuneParams& prm, cudaStream_t st) {
   int rc = NB_ERR_INVALID;
   char msg[256] = "";
+  if (p->dune_variant == 1) {
+    rc = nb::launch_dune_mma(prm, p->d_image, p->sm_count, p->max_smem_optin, st, msg, sizeof(msg));
+    if (rc) return fail(rc, "%s", msg);
+    ++g_launches;
+    return NB_OK;
+  }
   switch (p->cfg.edge_dim) {
 #define NB_CASE(E_)                                                                                        \
   case E_:                                                                                                 \
@@ -205,6 +221,10 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
     }
     NB_CUDA(dalloc(&p->d_weights, (size_t)n_weights));
     NB_CUDA(cudaMemcpy(p->d_weights, weights, (size_t)n_weights * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<unsigned char> image;
+    nb::build_mma_image(weights, cfg->edge_dim, image);
+    NB_CUDA(dalloc(&p->d_image, image.size()));
+    NB_CUDA(cudaMemcpy(p->d_image, image.data(), image.size(), cudaMemcpyHostToDevice));
   }
   NB_CUDA(dalloc(&p->sel_mu, B * T1 * M * E));
   NB_CUDA(dalloc(&p->sel_lam, B * T1 * M * 2));
@@ -231,7 +251,7 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
 int nb_pan_destroy(nb_pan_t* p) {
   if (!p) return NB_OK;
   cudaSetDevice(p->cfg.device);
-  void* bufs[] = {p->d_weights, p->sel_mu, p->sel_lam, p->sel_pts, p->sel_dist, p->sel_count, p->prev_s, p->prev_u, p->prev_mu,
+  void* bufs[] = {p->d_image, p->d_weights, p->sel_mu, p->sel_lam, p->sel_pts, p->sel_dist, p->sel_count, p->prev_s, p->prev_u, p->prev_mu,
                   p->prev_lam, p->prev_count, p->prev_valid, p->active, p->iters, p->status, p->min_dist, p->h_in, p->h_out, p->h_np, p->h_io};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -250,6 +270,16 @@ int nb_pan_set_iteration(nb_pan_t* p, int32_t iter_num, float iter_threshold) {
   if (!p || iter_num < 0) return fail(NB_ERR_INVALID, "bad argument");
   p->cfg.iter_num = iter_num; p->cfg.iter_threshold = iter_threshold;
   return NB_OK;
+}
+
+int nb_pan_set_option(nb_pan_t* p, int32_t option, int32_t value) {
+  if (!p) return fail(NB_ERR_INVALID, "null handle");
+  if (option == NB_OPT_DUNE_KERNEL) {
+    if (value != 0 && value != 1) return fail(NB_ERR_INVALID, "NB_OPT_DUNE_KERNEL takes 0 (fp32 ffma) or 1 (tensor core)");
+    p->dune_variant = value;
+    return NB_OK;
+  }
+  return fail(NB_ERR_INVALID, "unknown option %d", option);
 }
 
 int nb_pan_reset_state(nb_pan_t* p) {

@@ -33,12 +33,14 @@ def _oracle_dune(cfg, inp, b):
 
 
 @pytest.mark.parametrize("cname", ["C1", "C2", "C3", "C4", "C5"])
-def test_dune_half_matches_oracle(cname):
-    """DUNE kernel alone: the M closest points per (env, step), their mu, lam, distance."""
+@pytest.mark.parametrize("dune_kernel", [1, 0])
+def test_dune_half_matches_oracle(cname, dune_kernel):
+    """DUNE kernel alone (tensor-core and all-FP32 variants): the M closest points per (env, step),
+    their mu, lam, distance."""
     cfg = CONFIGS[cname]
     B = 6
     inp = make_inputs(cfg, B=B)
-    pan = make_pan(cfg, K=1, max_envs=B)
+    pan = make_pan(cfg, K=1, max_envs=B, dune_kernel=dune_kernel)
     run_pan(pan, inp)
     sel = {k: v.cpu().numpy() for k, v in pan.read_selection().items()}
     # NOTE: selections are those of the (single) executed iteration, computed from the input nom_s

@@ -1,0 +1,117 @@
+// Pipe-rate microbenchmarks on B200: legacy mma.sync (tf32 / f16 / bf16), FFMA, MUFU (ex2, rcp, tanh.approx).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench microbench.cu ; run on the GPU box.
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#define ITERS 4096
+#define ILP 8
+
+__global__ void k_mma_tf32(float* out) {
+  float c[ILP][4];
+  unsigned a[4] = {threadIdx.x, 2, 3, 4}, b[2] = {5, 6};
+  for (int i = 0; i < ILP; ++i) for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i)
+      asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  }
+  float s = 0; for (int i = 0; i < ILP; ++i) for (int j = 0; j < 4; ++j) s += c[i][j];
+  if (s == 123.f) out[0] = s;
+}
+__global__ void k_mma_f16(float* out) {
+  float c[ILP][4];
+  unsigned a[4] = {threadIdx.x, 2, 3, 4}, b[2] = {5, 6};
+  for (int i = 0; i < ILP; ++i) for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i)
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  }
+  float s = 0; for (int i = 0; i < ILP; ++i) for (int j = 0; j < 4; ++j) s += c[i][j];
+  if (s == 123.f) out[0] = s;
+}
+__global__ void k_mma_bf16(float* out) {
+  float c[ILP][4];
+  unsigned a[4] = {threadIdx.x, 2, 3, 4}, b[2] = {5, 6};
+  for (int i = 0; i < ILP; ++i) for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i)
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  }
+  float s = 0; for (int i = 0; i < ILP; ++i) for (int j = 0; j < 4; ++j) s += c[i][j];
+  if (s == 123.f) out[0] = s;
+}
+__global__ void k_ffma(float* out) {
+  float c[ILP]; float a = threadIdx.x * 1e-9f, b = 0.999f;
+  for (int i = 0; i < ILP; ++i) c[i] = i;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) c[i] = fmaf(c[i], b, a);
+  }
+  float s = 0; for (int i = 0; i < ILP; ++i) s += c[i];
+  if (s == 123.f) out[0] = s;
+}
+template <int OP>
+__global__ void k_mufu(float* out) {
+  float c[ILP];
+  for (int i = 0; i < ILP; ++i) c[i] = 0.5f + i * 0.01f + threadIdx.x * 1e-6f;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+      if (OP == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(c[i]));
+      if (OP == 1) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(c[i]));
+      if (OP == 2) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(c[i]));
+      if (OP == 3) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(c[i]));
+    }
+  }
+  float s = 0; for (int i = 0; i < ILP; ++i) s += c[i];
+  if (s == 123.f) out[0] = s;
+}
+__global__ void k_dfma(double* out) {
+  double c[ILP]; double a = threadIdx.x * 1e-9, b = 0.999;
+  for (int i = 0; i < ILP; ++i) c[i] = i;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) c[i] = fma(c[i], b, a);
+  }
+  double s = 0; for (int i = 0; i < ILP; ++i) s += c[i];
+  if (s == 123.0) out[0] = s;
+}
+
+template <typename F> float timeit(F f) {
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  f(); cudaDeviceSynchronize();
+  cudaEventRecord(a); f(); cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b); return ms;
+}
+
+int main() {
+  int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+  float* d; cudaMalloc(&d, 1024); double* dd; cudaMalloc(&dd, 1024);
+  printf("SMs %d, clock attr %d kHz\n", sms, clk);
+  for (int wps : {4, 8, 16, 32}) {
+    const int threads = 256, blocks = sms * (wps * 32 / threads > 0 ? wps * 32 / threads : 1);
+    const int th = wps * 32 < threads ? wps * 32 : threads;
+    const double warps = (double)blocks * th / 32;
+    auto rep = [&](const char* name, float ms, double work_per_warp_iter, const char* unit) {
+      double per_s = warps * ITERS * ILP * work_per_warp_iter / (ms * 1e-3);
+      printf("  warps/SM %2d %-12s %8.3f ms  %10.1f G%s/s  (%.0f per clk per SM @1.965GHz)\n", wps, name, ms, per_s / 1e9, unit, per_s / sms / 1.965e9);
+    };
+    rep("mma tf32", timeit([&] { k_mma_tf32<<<blocks, th>>>(d); }), 16 * 8 * 8, "MAC");
+    rep("mma f16", timeit([&] { k_mma_f16<<<blocks, th>>>(d); }), 16 * 8 * 16, "MAC");
+    rep("mma bf16", timeit([&] { k_mma_bf16<<<blocks, th>>>(d); }), 16 * 8 * 16, "MAC");
+    rep("ffma", timeit([&] { k_ffma<<<blocks, th>>>(d); }), 32, "FMA");
+    rep("dfma", timeit([&] { k_dfma<<<blocks, th>>>(dd); }), 32, "FMA");
+    rep("ex2", timeit([&] { k_mufu<0><<<blocks, th>>>(d); }), 32, "op");
+    rep("rcp", timeit([&] { k_mufu<1><<<blocks, th>>>(d); }), 32, "op");
+    rep("tanh.approx", timeit([&] { k_mufu<2><<<blocks, th>>>(d); }), 32, "op");
+    rep("rsqrt", timeit([&] { k_mufu<3><<<blocks, th>>>(d); }), 32, "op");
+  }
+  return 0;
+}
