@@ -129,6 +129,9 @@ int nb_pan_reset_state(nb_pan_t* pan);
 int nb_pan_read_selection(nb_pan_t* pan, int32_t B, float* sel_mu, float* sel_lam, float* sel_points,
                           float* sel_distance, int32_t* sel_count, void* stream);
 
+/* Diagnostics of the last executed NRMP solve: interior point iterations per env (B) int32. */
+int nb_pan_read_diagnostics(nb_pan_t* pan, int32_t B, int32_t* ipm_iterations, void* stream);
+
 /* ---- the two halves, exposed separately (parity tests, profiling) ------------------------ */
 
 /* PAN.generate_point_flow + DUNE.forward (pan.py:150-212, dune.py:58-127) for B envs, keeping the

@@ -45,6 +45,7 @@ SYMBOLS = {
     "nb_pan_set_option": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "nb_pan_reset_state": (C.c_int, [C.c_void_p]),
     "nb_pan_read_selection": (C.c_int, [C.c_void_p, C.c_int32] + [_FP] * 5 + [C.c_void_p]),
+    "nb_pan_read_diagnostics": (C.c_int, [C.c_void_p, C.c_int32, _FP, C.c_void_p]),
     "nb_dune_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [_FP] * 5 + [C.c_void_p]),
     "nb_nrmp_forward": (C.c_int, [C.c_void_p, C.c_int32] + [_FP] * 10 + [C.c_void_p]),
     "nb_launch_count": (C.c_int64, []),

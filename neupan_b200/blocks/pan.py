@@ -203,6 +203,17 @@ class PAN(torch.nn.Module):
         """Per-environment solver status bits of the last forward (0 = ok)."""
         return None if self._last is None else self._last["status"]
 
+    @property
+    def ipm_iterations(self):
+        """Interior point iterations of the last NRMP solve per environment (diagnostics)."""
+        if self._last is None:
+            return None
+        out = torch.empty(self._last["B"], dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(_lib.load().nb_pan_read_diagnostics(self._handle, self._last["B"], _ptr(out), stream))
+        return out
+
     def read_selection(self):
         """The M closest points per (env, step) of the last executed iteration, ascending distance:
         dict(mu (B,T+1,M,E), lam (B,T+1,M,2), points (B,T+1,M,2), distance (B,T+1,M), count (B))."""

@@ -13,13 +13,17 @@
 // predictor-corrector primal-dual interior point method runs in FP64 from a strictly feasible
 // start.  Inside each Newton step the T*M hinge slacks and the T distances D_t are eliminated
 // analytically (both blocks are diagonal), so the only factorisation is a dense 2T x 2T Cholesky
-// held in the warp's shared memory.  Rows of every matrix are owned by lanes; all
-// synchronisation is __syncwarp, a warp can finish early without affecting its neighbours.
+// in the warp's shared memory.
+//
+// Mapping: lanes own rows of the 2T x 2T system (triangular solves run in registers with
+// shuffles), lanes own HPL hinge rows each whose slack/multiplier state lives in registers, lanes
+// own horizon steps for the per-step reductions.  Inverse slacks and step ratios are float (they only
+// shape the Newton direction / step length; residuals and iterates are FP64), reciprocals use
+// rcp.approx + Newton.  All synchronisation is __syncwarp; a warp finishes independently.
 #pragma once
 #include "common.cuh"
 
 namespace nb {
-
 struct NrmpParams {
   const float* nom_s;   // (B,3,T+1) nominal states in
   const float* nom_u;   // (B,2,T)
@@ -36,6 +40,7 @@ struct NrmpParams {
   float* out_d;         // (B,T)
   int32_t* status;      // (B) or nullptr
   int32_t* iters;       // (B) or nullptr: incremented per executed iteration
+  int32_t* ipm_iters;   // (B) or nullptr: interior point iterations of this solve (diagnostics)
   int32_t* active;      // (B) or nullptr: envs with 0 are skipped; cleared when the stop test fires
   // PAN.current_nom_values (pan.py:100-105), per env; nullptr disables the stop criterion
   float* prev_s; float* prev_u; float* prev_mu; float* prev_lam; int32_t* prev_count; int32_t* prev_valid;
@@ -49,21 +54,33 @@ struct NrmpParams {
   float h[kMaxEdges];
 };
 
+
+// per-warp shared memory, in doubles
+__host__ __device__ inline size_t nrmp_scratch_doubles(int T, int M) {
+  size_t sc = 2 * (size_t)T * (2 * T);  // Gx,Gy; also holds per-hinge scratch (T*M) and the setup-only linearisation (12 T)
+  if (sc < (size_t)T * M) sc = (size_t)T * M;
+  if (sc < 12 * (size_t)T) sc = 12 * (size_t)T;
+  return sc;
+}
 __host__ __device__ inline size_t nrmp_warp_doubles(int T, int M) {
   const int nU = 2 * T, nR = nU - 2, TD = M > 0 ? T : 0, TM = T * M;
-  const int m = 2 * nU + 2 * nR + 2 * TD + 2 * TM;
+  const int mb = 2 * nU + 2 * nR + 2 * TD;
   size_t n = 0;
-  n += 3 * (size_t)T * nU;        // F
-  n += 3 * (size_t)T;             // s0
-  n += (size_t)nU * (nU + 1) / 2; // Hc
-  n += (size_t)nU * (nU + 1);     // H (padded rows)
-  n += 2 * (size_t)T * nU;        // Gx, Gy
-  n += 6 * (size_t)nU;            // c, x, dU, rhs, rdU, invd
-  n += 18 * (size_t)T;            // per-step scalars
-  n += 4 * (size_t)m;             // s, z, ds, dz
-  n += 6 * (size_t)TM;            // fax, fay, kk, wrh, iHww, bw
-  n += 11 * (size_t)T;            // linearisation a02,a12,B(6),C(3)
-  return n + 8;
+  n += 3 * (size_t)T * nU;         // F
+  n += 3 * (size_t)T;              // s0
+  n += (size_t)nU * (nU + 1) / 2;  // Hc
+  n += (size_t)nU * (nU + 1);      // H (padded rows)
+  n += nrmp_scratch_doubles(T, M);
+  n += 4 * (size_t)nU;             // cv, x, rdU, dU
+  n += 14 * (size_t)T;             // per-step scalars
+  n += 4 * (size_t)mb;             // s, z, ds, dz of the box / rate / D rows
+  n += ((size_t)mb + 1) / 2;       // is (float)
+  n += (size_t)TM;                 // fax, fay (float)
+  return n + 4;
+}
+__host__ __device__ inline size_t nrmp_cta_extra_bytes(int T) {  // pair table (uint16) shared by the CTA's warps
+  const int nU = 2 * T;
+  return (((size_t)nU * (nU + 1) / 2) * 2 + 15) / 16 * 16;
 }
 
 #define NB_LL(i, n) for (int i = lane; i < (n); i += 32)
@@ -73,44 +90,71 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ double warp_min(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+__device__ __forceinline__ float warp_maxf(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// 1/x for a normal positive double: hardware seed (~20 bits) + two Newton steps
+__device__ __forceinline__ double rcp64(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+// 1/sqrt(x) for a positive double inside float range: float seed + three Newton steps
+__device__ __forceinline__ double rsqrt64(double x) {
+  double r = (double)rsqrtf((float)x);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r = r * fma(-0.5 * x, r * r, 1.5);
+  return r;
+}
+__device__ __forceinline__ float rcpf(double x) { return __frcp_rn((float)x); }
 
-__global__ void __launch_bounds__(256) nrmp_kernel(const NrmpParams prm, int warps_per_cta, int warp_doubles) {
+template <int HPL>
+__global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpParams prm, int warps_per_cta, int warp_doubles) {
   extern __shared__ __align__(16) double smem_d[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int T = prm.T, M = prm.M, T1 = T + 1;
+  const int nU = 2 * T, nR = nU - 2, TD = M > 0 ? T : 0, TM = T * M;
+  const int nP = nU * (nU + 1) / 2;
+  const int oBU = 0, oBL = nU, oRU = 2 * nU, oRL = oRU + nR, oDU = oRL + nR, oDL = oDU + TD;
+  const int mb = oDL + TD;
+  const int HS = nU + 1;
+
+  // pair table (i << 8 | j) of the lower triangle, shared by the CTA
+  unsigned short* ptab = reinterpret_cast<unsigned short*>(smem_d + (size_t)warps_per_cta * warp_doubles);
+  for (int p = threadIdx.x; p < nP; p += blockDim.x) {
+    int i = (int)((sqrtf(8.0f * p + 1.0f) - 1.0f) * 0.5f);
+    while (i * (i + 1) / 2 > p) --i;
+    while ((i + 1) * (i + 2) / 2 <= p) ++i;
+    ptab[p] = (unsigned short)((i << 8) | (p - i * (i + 1) / 2));
+  }
+  __syncthreads();
+
   const int b = blockIdx.x * warps_per_cta + warp;
   if (b >= prm.B) return;
   if (prm.active && prm.active[b] == 0) return;
-
-  const int T = prm.T, M = prm.M, T1 = T + 1;
-  const int nU = 2 * T, nR = nU - 2, TD = M > 0 ? T : 0, TM = T * M;
-  const int oBU = 0, oBL = nU, oRU = 2 * nU, oRL = oRU + nR, oDU = oRL + nR, oDL = oDU + TD, oHW = oDL + TD, oHR = oHW + TM;
-  const int m = oHR + TM;
-  const int HS = nU + 1;  // row stride of H
 
   // ---- carve this warp's workspace -------------------------------------------------------
   double* wsp = smem_d + (size_t)warp * warp_doubles;
   double* F = wsp;            wsp += 3 * T * nU;   // F[r][t][j]
   double* s0 = wsp;           wsp += 3 * T;        // s0[r][t]
-  double* Hc = wsp;           wsp += nU * (nU + 1) / 2;
+  double* Hc = wsp;           wsp += nP;
   double* H = wsp;            wsp += nU * HS;
-  double* Gx = wsp;           wsp += T * nU;
-  double* Gy = wsp;           wsp += T * nU;
+  double* scratch = wsp;      wsp += nrmp_scratch_doubles(T, M);
+  double* Gx = scratch;  double* Gy = scratch + T * nU;  // Hessian assembly
+  double* tmpk = scratch;                                // per-hinge values published for the per-step sums
   double* cv = wsp;           wsp += nU;
   double* x = wsp;            wsp += nU;
-  double* dU = wsp;           wsp += nU;
-  double* rhs = wsp;          wsp += nU;
   double* rdU = wsp;          wsp += nU;
-  double* invd = wsp;         wsp += nU;
+  double* dU = wsp;           wsp += nU;
   double* Dv = wsp;           wsp += T;
   double* dD = wsp;           wsp += T;
   double* rdD = wsp;          wsp += T;
@@ -125,24 +169,16 @@ __global__ void __launch_bounds__(256) nrmp_kernel(const NrmpParams prm, int war
   double* e1 = wsp;           wsp += T;
   double* qx = wsp;           wsp += T;
   double* qy = wsp;           wsp += T;
-  double* gt0 = wsp;          wsp += T;
-  double* gt1 = wsp;          wsp += T;
-  double* gam_b = wsp;        wsp += T;
-  wsp += T;  // spare
-  double* cs = wsp;           wsp += m;   // slacks
-  double* cz = wsp;           wsp += m;   // multipliers
-  double* cds = wsp;          wsp += m;
-  double* cdz = wsp;          wsp += m;   // holds rc on entry of a Newton solve, dz on exit
-  double* fax = wsp;          wsp += TM;
-  double* fay = wsp;          wsp += TM;
-  double* kk = wsp;           wsp += TM;
-  double* wrh = wsp;          wsp += TM;
-  double* iHww = wsp;         wsp += TM;
-  double* bw = wsp;           wsp += TM;
-  double* a02 = wsp;          wsp += T;
-  double* a12 = wsp;          wsp += T;
-  double* Bm = wsp;           wsp += 6 * T;
-  double* Cm = wsp;           wsp += 3 * T;
+  double* cs = wsp;           wsp += mb;   // slacks of the box / rate / D rows
+  double* cz = wsp;           wsp += mb;   // multipliers
+  double* cds = wsp;          wsp += mb;
+  double* cdz = wsp;          wsp += mb;   // holds rc on entry of a Newton solve, dz on exit
+  float* cis = reinterpret_cast<float*>(wsp);  wsp += (mb + 1) / 2;  // inverse slacks
+  float* fax_s = reinterpret_cast<float*>(wsp);
+  float* fay_s = fax_s + TM;
+  // setup-only linearisation data lives in the scratch region
+  double* a02 = scratch;      double* a12 = scratch + T;  double* Bm = scratch + 2 * T;  double* Cm = scratch + 8 * T;
+  double* gam_b = scratch + 11 * T;
 
   const float* ns = prm.nom_s + (size_t)b * 3 * T1;
   const float* nu = prm.nom_u + (size_t)b * 2 * T;
@@ -152,13 +188,14 @@ __global__ void __launch_bounds__(256) nrmp_kernel(const NrmpParams prm, int war
   const int rows_s = omni ? 2 : 3;
   const bool en_speed[2] = {isfinite(prm.speed[0]), isfinite(prm.speed[1])};
   const bool en_acce[2] = {isfinite(prm.acce[0]), isfinite(prm.acce[1])};
-  auto enabled = [&](int k) -> bool {
+  auto enabled = [&](int k) -> bool {  // rows of the shared-memory constraint block
     if (k < oRU) return en_speed[(k % nU) & 1];
     if (k < oDU) return en_acce[((k - oRU) % nR) & 1];
     return true;
   };
   int m_active = 2 * TD + 2 * TM;
   for (int c = 0; c < 2; ++c) m_active += (en_speed[c] ? 2 * T : 0) + (en_acce[c] ? 2 * (T - 1) : 0);
+  const double inv_m = 1.0 / (double)(m_active > 0 ? m_active : 1);
 
   // ---- 1. kinematics linearisation (robot.py:272-316, float32 tensor semantics) -------------
   const float fdt = (float)prm.dt;
@@ -234,46 +271,53 @@ __global__ void __launch_bounds__(256) nrmp_kernel(const NrmpParams prm, int war
     if ((j & 1) == 0) acc += -2.0 * pu * gam_b[j >> 1];
     cv[j] = acc;
   }
-  for (int p = lane; p < nU * (nU + 1) / 2; p += 32) {
-    int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
-    while (i * (i + 1) / 2 > p) --i;
-    while ((i + 1) * (i + 2) / 2 <= p) ++i;
-    const int j = p - i * (i + 1) / 2;
+  NB_LL(p, nP) {
+    const int i = ptab[p] >> 8, j = ptab[p] & 255;
     double acc = 0;
     for (int t = i >> 1; t < T; ++t)
       for (int r = 0; r < 3; ++r) acc += qd[r] * F[(r * T + t) * nU + i] * F[(r * T + t) * nU + j];
     if (i == j && (i & 1) == 0) acc += 2.0 * pu * pu;
     Hc[p] = acc;
   }
+  __syncwarp();  // the linearisation data in `scratch` is dead from here on
 
-  // ---- 4. obstacle coefficients (nrmp.py:220-261) ---------------------------------------------
-  const int cnt = (prm.fa || M == 0) ? M : (prm.sel_count ? prm.sel_count[b] : 0);
-  NB_LL(k, TM) {
-    const int t = k / M, mm = k - t * M;
-    float fx = 0.f, fy = 0.f, fbv = 0.f;
-    if (prm.fa) {
-      fx = prm.fa[((size_t)b * TM + k) * 2]; fy = prm.fa[((size_t)b * TM + k) * 2 + 1]; fbv = prm.fb[(size_t)b * TM + k];
-    } else if (cnt > 0) {
-      const int src = mm < cnt ? mm : 0;  // rows pn..M copy row 0 (nrmp.py:258-259)
-      const size_t o = ((size_t)b * T1 + (t + 1)) * M + src;  // list entry t+1 (nrmp.py:244)
-      fx = prm.sel_lam[o * 2]; fy = prm.sel_lam[o * 2 + 1];
-      const float tmp = __fadd_rn(__fmul_rn(fx, prm.sel_pts[o * 2]), __fmul_rn(fy, prm.sel_pts[o * 2 + 1]));
-      float muh = 0.f;
-      for (int e = 0; e < prm.E; ++e) muh = fmaf(prm.sel_mu[o * prm.E + e], prm.h[e], muh);
-      fbv = __fadd_rn(tmp, muh);
-    }
-    fax[k] = fx; fay[k] = fy;
-    kk[k] = (double)fbv;  // completed with -fa.s0 below
-  }
-  __syncwarp();
-  NB_LL(k, TM) {
-    const int t = k / M;
-    kk[k] -= fax[k] * s0[t] + fay[k] * s0[T + t];
-  }
-
-  // ---- 5. strictly feasible start -------------------------------------------------------------
+  // ---- 4. obstacle coefficients (nrmp.py:220-261), hinge rows owned by lanes -----------------------
   const double rho = prm.ro, eta = (double)prm.eta;
   const double dlo = fmax((double)prm.d_min, 0.0), dhi = (double)prm.d_max;
+  const int cnt = (prm.fa || M == 0) ? M : (prm.sel_count ? prm.sel_count[b] : 0);
+  float hfx[HPL], hfy[HPL];
+  double hsw[HPL], hsr[HPL], hzw[HPL], hzr[HPL], hdsw[HPL], hdsr[HPL], hdzw[HPL], hdzr[HPL];
+  float hisw[HPL], hisr[HPL];
+  double hih[HPL];  // 1/H_ww must be FP64: the slack elimination has to be exact for the Newton system to stay consistent
+#pragma unroll
+  for (int q_ = 0; q_ < HPL; ++q_) {
+    const int k = lane + 32 * q_;
+    hfx[q_] = 0.f; hfy[q_] = 0.f; hsw[q_] = 1.0; hsr[q_] = 1.0; hzw[q_] = 0.0; hzr[q_] = 0.0;
+    hdsw[q_] = hdsr[q_] = hdzw[q_] = hdzr[q_] = 0.0; hisw[q_] = hisr[q_] = 0.f; hih[q_] = 0.0;
+    if (k < TM) {
+      const int t = k / M, mm = k - t * M;
+      float fx = 0.f, fy = 0.f, fbv = 0.f;
+      if (prm.fa) {
+        fx = prm.fa[((size_t)b * TM + k) * 2]; fy = prm.fa[((size_t)b * TM + k) * 2 + 1]; fbv = prm.fb[(size_t)b * TM + k];
+      } else if (cnt > 0) {
+        const int src = mm < cnt ? mm : 0;  // rows pn..M copy row 0 (nrmp.py:258-259)
+        const size_t o = ((size_t)b * T1 + (t + 1)) * M + src;  // list entry t+1 (nrmp.py:244)
+        fx = prm.sel_lam[o * 2]; fy = prm.sel_lam[o * 2 + 1];
+        const float tmp = __fadd_rn(__fmul_rn(fx, prm.sel_pts[o * 2]), __fmul_rn(fy, prm.sel_pts[o * 2 + 1]));
+        float muh = 0.f;
+        for (int e = 0; e < prm.E; ++e) muh = fmaf(prm.sel_mu[o * prm.E + e], prm.h[e], muh);
+        fbv = __fadd_rn(tmp, muh);
+      }
+      hfx[q_] = fx; hfy[q_] = fy;
+      fax_s[k] = fx; fay_s[k] = fy;
+      const double kk = (double)fbv - ((double)fx * s0[t] + (double)fy * s0[T + t]);
+      const double r = 0.5 * (dlo + dhi) + kk;  // hinge argument at the start (u = 0, D mid-range)
+      const double w = fmax(r, 0.0) + 1.0;
+      hsw[q_] = w; hsr[q_] = w - r; hzw[q_] = 1.0 / w; hzr[q_] = 1.0 / (w - r);
+    }
+  }
+
+  // ---- 5. strictly feasible start of the remaining rows --------------------------------------------
   int stat = 0;
   if (TD > 0 && !(dhi > dlo)) stat |= 4;
   for (int c = 0; c < 2; ++c) {
@@ -295,133 +339,32 @@ __global__ void __launch_bounds__(256) nrmp_kernel(const NrmpParams prm, int war
     cs[oDU + t] = dhi - Dv[t]; cs[oDL + t] = Dv[t] - dlo;
     cz[oDU + t] = 1.0 / cs[oDU + t]; cz[oDL + t] = 1.0 / cs[oDL + t];
   }
-  NB_LL(k, TM) {
-    const double r = 0.5 * (dlo + dhi) + kk[k];
-    const double w = fmax(r, 0.0) + 1.0;
-    cs[oHW + k] = w; cs[oHR + k] = w - r;
-    cz[oHW + k] = 1.0 / w; cz[oHR + k] = 1.0 / (w - r);
-  }
   __syncwarp();
-
-  // One Newton solve with the factorised H: reads rc from cdz, writes dU, dD, cds, cdz.
-  auto newton = [&]() {
-    NB_LL(k, TM) {
-      const double vw = cdz[oHW + k] / cs[oHW + k], vr = cdz[oHR + k] / cs[oHR + k];
-      const double rdw = rho * cs[oHW + k] - cz[oHW + k] - cz[oHR + k];
-      const double b_w = -rdw + vw + vr;
-      bw[k] = b_w;
-    }
-    __syncwarp();
-    NB_LL(t, TD) {
-      double Y0 = 0, Y1 = 0, Ys = 0;
-      for (int mm = 0; mm < M; ++mm) {
-        const int k = t * M + mm;
-        const double y = wrh[k] * bw[k] - cdz[oHR + k] / cs[oHR + k];
-        Y0 += y * fax[k]; Y1 += y * fay[k]; Ys += y;
-      }
-      const double vdu = cdz[oDU + t] / cs[oDU + t], vdl = cdz[oDL + t] / cs[oDL + t];
-      const double b = -rdD[t] - (vdu - vdl) + Ys;
-      bD[t] = b;
-      e0[t] = -Y0 + n0[t] * b * iHDD[t];
-      e1[t] = -Y1 + n1[t] * b * iHDD[t];
-    }
-    __syncwarp();
-    NB_LL(i, nU) {
-      double acc = -rdU[i] - (cdz[oBU + i] / cs[oBU + i] - cdz[oBL + i] / cs[oBL + i]);
-      if (i >= 2) acc -= cdz[oRU + i - 2] / cs[oRU + i - 2] - cdz[oRL + i - 2] / cs[oRL + i - 2];
-      if (i < nR) acc += cdz[oRU + i] / cs[oRU + i] - cdz[oRL + i] / cs[oRL + i];
-      if (TD > 0)
-        for (int t = i >> 1; t < T; ++t) acc += F[(0 * T + t) * nU + i] * e0[t] + F[(1 * T + t) * nU + i] * e1[t];
-      rhs[i] = acc;
-    }
-    __syncwarp();
-    // forward / backward substitution with the Cholesky factor in H (lower), invd = 1/diag
-    for (int k = 0; k < nU; ++k) {
-      const double yk = rhs[k] * invd[k];
-      __syncwarp();
-      NB_LL(i, nU) {
-        if (i > k) rhs[i] -= H[i * HS + k] * yk;
-        else if (i == k) rhs[i] = yk;
-      }
-      __syncwarp();
-    }
-    for (int k = nU - 1; k >= 0; --k) {
-      const double yk = rhs[k] * invd[k];
-      __syncwarp();
-      NB_LL(i, nU) {
-        if (i < k) rhs[i] -= H[k * HS + i] * yk;
-        else if (i == k) rhs[i] = yk;
-      }
-      __syncwarp();
-    }
-    NB_LL(i, nU) dU[i] = rhs[i];
-    __syncwarp();
-    NB_LL(t, TD) {
-      double ax = 0, ay = 0;
-      for (int i = 0; i < 2 * (t + 1); ++i) {
-        ax += F[(0 * T + t) * nU + i] * dU[i];
-        ay += F[(1 * T + t) * nU + i] * dU[i];
-      }
-      qx[t] = ax; qy[t] = ay;
-      dD[t] = (bD[t] + n0[t] * ax + n1[t] * ay) * iHDD[t];
-    }
-    __syncwarp();
-    NB_LL(k, TM) {
-      const int t = k / M;
-      const double Jdx = dD[t] - (fax[k] * qx[t] + fay[k] * qy[t]);
-      const double dw = bw[k] * iHww[k] + wrh[k] * Jdx;
-      const double dsw = dw, dsr = dw - Jdx;
-      cdz[oHW + k] = (cdz[oHW + k] - cz[oHW + k] * dsw) / cs[oHW + k];
-      cdz[oHR + k] = (cdz[oHR + k] - cz[oHR + k] * dsr) / cs[oHR + k];
-      cds[oHW + k] = dsw; cds[oHR + k] = dsr;
-    }
-    NB_LL(i, nU) {
-      const double d = dU[i];
-      cdz[oBU + i] = (cdz[oBU + i] + cz[oBU + i] * d) / cs[oBU + i]; cds[oBU + i] = -d;
-      cdz[oBL + i] = (cdz[oBL + i] - cz[oBL + i] * d) / cs[oBL + i]; cds[oBL + i] = d;
-      if (i < nR) {
-        const double dd = dU[i + 2] - d;
-        cdz[oRU + i] = (cdz[oRU + i] + cz[oRU + i] * dd) / cs[oRU + i]; cds[oRU + i] = -dd;
-        cdz[oRL + i] = (cdz[oRL + i] - cz[oRL + i] * dd) / cs[oRL + i]; cds[oRL + i] = dd;
-      }
-    }
-    NB_LL(t, TD) {
-      const double d = dD[t];
-      cdz[oDU + t] = (cdz[oDU + t] + cz[oDU + t] * d) / cs[oDU + t]; cds[oDU + t] = -d;
-      cdz[oDL + t] = (cdz[oDL + t] - cz[oDL + t] * d) / cs[oDL + t]; cds[oDL + t] = d;
-    }
-    __syncwarp();
-  };
-
-  auto max_step = [&]() -> double {
-    double a = 1.0;
-    NB_LL(k, m) {
-      if (!enabled(k)) continue;
-      const double ds = cds[k], dz = cdz[k];
-      if (ds < 0) a = fmin(a, -cs[k] / ds);
-      if (dz < 0) a = fmin(a, -cz[k] / dz);
-    }
-    return warp_min(a);
-  };
 
   // ---- 6. interior point iterations -------------------------------------------------------------
   int it = 0;
   bool converged = false;
   if (stat == 0) {
     for (it = 0; it < prm.max_ipm_iter; ++it) {
-      // dual residual
+      // (a) dual residual, gap
+#pragma unroll
+      for (int q_ = 0; q_ < HPL; ++q_) {
+        const int k = lane + 32 * q_;
+        if (k < TM) tmpk[k] = hzr[q_];
+      }
+      __syncwarp();
       NB_LL(t, TD) {
         double gx = 0, gy = 0, sz = 0;
         for (int mm = 0; mm < M; ++mm) {
           const int k = t * M + mm;
-          const double zr = cz[oHR + k];
-          gx += zr * fax[k]; gy += zr * fay[k]; sz += zr;
+          const double zr = tmpk[k];
+          gx += zr * (double)fax_s[k]; gy += zr * (double)fay_s[k]; sz += zr;
         }
-        gt0[t] = gx; gt1[t] = gy;
+        e0[t] = gx; e1[t] = gy;  // (e0/e1 carry g_t here; rewritten inside the Newton solve)
         rdD[t] = -eta + cz[oDU + t] - cz[oDL + t] + sz;
       }
       __syncwarp();
-      double res = 0.0;
+      double res = 0.0, gsum = 0.0;
       NB_LL(i, nU) {
         double acc = cv[i];
         for (int j = 0; j < nU; ++j) {
@@ -432,33 +375,48 @@ __global__ void __launch_bounds__(256) nrmp_kernel(const NrmpParams prm, int war
         if (i >= 2) acc += cz[oRU + i - 2] - cz[oRL + i - 2];
         if (i < nR) acc -= cz[oRU + i] - cz[oRL + i];
         if (TD > 0)
-          for (int t = i >> 1; t < T; ++t) acc -= F[(0 * T + t) * nU + i] * gt0[t] + F[(1 * T + t) * nU + i] * gt1[t];
+          for (int t = i >> 1; t < T; ++t) acc -= F[(0 * T + t) * nU + i] * e0[t] + F[(1 * T + t) * nU + i] * e1[t];
         rdU[i] = acc;
         res = fmax(res, fabs(acc));
       }
       NB_LL(t, TD) res = fmax(res, fabs(rdD[t]));
-      double gsum = 0.0;
-      NB_LL(k, m) if (enabled(k)) gsum += cs[k] * cz[k];
-      NB_LL(k, TM) res = fmax(res, fabs(rho * cs[oHW + k] - cz[oHW + k] - cz[oHR + k]));
+      NB_LL(k, mb) if (enabled(k)) gsum += cs[k] * cz[k];
+#pragma unroll
+      for (int q_ = 0; q_ < HPL; ++q_) {
+        if (lane + 32 * q_ < TM) {
+          gsum += hsw[q_] * hzw[q_] + hsr[q_] * hzr[q_];
+          res = fmax(res, fabs(rho * hsw[q_] - hzw[q_] - hzr[q_]));
+        }
+      }
       res = warp_max(res);
-      const double gap = warp_sum(gsum) / (double)(m_active > 0 ? m_active : 1);
+      const double gap = warp_sum(gsum) * inv_m;
       if (!(gap == gap) || !(res == res)) { stat |= 2; break; }
       if (gap < 1e-10 && res < 1e-8) { converged = true; break; }
 
-      // barrier weights, per-step reductions, D elimination
+      // (b) barrier weights; hinge rows publish omega for the per-step reductions
+      __syncwarp();
+      NB_LL(k, mb) cis[k] = rcpf(cs[k]);
+#pragma unroll
+      for (int q_ = 0; q_ < HPL; ++q_) {
+        const int k = lane + 32 * q_;
+        if (k < TM) {
+          hisw[q_] = rcpf(hsw[q_]); hisr[q_] = rcpf(hsr[q_]);
+          const double Ww = hzw[q_] * (double)hisw[q_], Wr = hzr[q_] * (double)hisr[q_];
+          hih[q_] = rcp64(rho + Ww + Wr);
+          tmpk[k] = Wr * (rho + Ww) * hih[q_];
+        }
+      }
+      __syncwarp();
       NB_LL(t, TD) {
         double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0, nn = 0;
         for (int mm = 0; mm < M; ++mm) {
           const int k = t * M + mm;
-          const double Ww = cz[oHW + k] / cs[oHW + k], Wr = cz[oHR + k] / cs[oHR + k];
-          const double ih = 1.0 / (rho + Ww + Wr);
-          const double om = Wr * (rho + Ww) * ih;
-          wrh[k] = Wr * ih; iHww[k] = ih;
-          const double fx = fax[k], fy = fay[k];
-          a00 += om * fx * fx; a01 += om * fx * fy; a11 += om * fy * fy; b0 += om * fx; b1 += om * fy; nn += om;
+          const double om = tmpk[k], fx = (double)fax_s[k], fy = (double)fay_s[k];
+          const double ofx = om * fx, ofy = om * fy;
+          a00 += ofx * fx; a01 += ofx * fy; a11 += ofy * fy; b0 += ofx; b1 += ofy; nn += om;
         }
-        const double hdd = nn + cz[oDU + t] / cs[oDU + t] + cz[oDL + t] / cs[oDL + t];
-        const double ih = 1.0 / hdd;
+        const double hdd = nn + cz[oDU + t] * (double)cis[oDU + t] + cz[oDL + t] * (double)cis[oDL + t];
+        const double ih = rcp64(hdd);
         iHDD[t] = ih; n0[t] = b0; n1[t] = b1;
         N00[t] = a00 - b0 * b0 * ih; N01[t] = a01 - b0 * b1 * ih; N11[t] = a11 - b1 * b1 * ih;
       }
@@ -472,67 +430,192 @@ __global__ void __launch_bounds__(256) nrmp_kernel(const NrmpParams prm, int war
           }
         __syncwarp();
       }
-      // assemble the reduced Hessian (lower triangle)
-      for (int p = lane; p < nU * (nU + 1) / 2; p += 32) {
-        int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
-        while (i * (i + 1) / 2 > p) --i;
-        while ((i + 1) * (i + 2) / 2 <= p) ++i;
-        const int j = p - i * (i + 1) / 2;
+      // (c) reduced Hessian, lower triangle
+      NB_LL(p, nP) {
+        const int i = ptab[p] >> 8, j = ptab[p] & 255;
         double acc = Hc[p];
         if (TD > 0)
           for (int t = i >> 1; t < T; ++t) acc += F[(0 * T + t) * nU + i] * Gx[t * nU + j] + F[(1 * T + t) * nU + i] * Gy[t * nU + j];
         if (i == j) {
-          acc += cz[oBU + i] / cs[oBU + i] + cz[oBL + i] / cs[oBL + i];
-          if (i >= 2) acc += cz[oRU + i - 2] / cs[oRU + i - 2] + cz[oRL + i - 2] / cs[oRL + i - 2];
-          if (i < nR) acc += cz[oRU + i] / cs[oRU + i] + cz[oRL + i] / cs[oRL + i];
+          acc += cz[oBU + i] * (double)cis[oBU + i] + cz[oBL + i] * (double)cis[oBL + i];
+          if (i >= 2) acc += cz[oRU + i - 2] * (double)cis[oRU + i - 2] + cz[oRL + i - 2] * (double)cis[oRL + i - 2];
+          if (i < nR) acc += cz[oRU + i] * (double)cis[oRU + i] + cz[oRL + i] * (double)cis[oRL + i];
         } else if (i == j + 2) {
-          acc -= cz[oRU + j] / cs[oRU + j] + cz[oRL + j] / cs[oRL + j];
+          acc -= cz[oRU + j] * (double)cis[oRU + j] + cz[oRL + j] * (double)cis[oRL + j];
         }
         H[i * HS + j] = acc;
       }
       __syncwarp();
-      // Cholesky, left-looking by column; lanes own rows
+      // (d) Cholesky, left-looking by column; lane owns rows lane, lane+32; inverse diagonal in registers
       bool bad = false;
+      double invd0 = 0.0, invd1 = 0.0;
       for (int k = 0; k < nU; ++k) {
-        NB_LL(i, nU) {
-          if (i >= k) {
-            double acc = H[i * HS + k];
-            for (int p = 0; p < k; ++p) acc -= H[i * HS + p] * H[k * HS + p];
-            H[i * HS + k] = acc;
-          }
+        double acc0 = 0.0, acc1 = 0.0;
+        const int i0 = lane, i1 = lane + 32;
+        if (i0 >= k && i0 < nU) {
+          acc0 = H[i0 * HS + k];
+          for (int p = 0; p < k; ++p) acc0 -= H[i0 * HS + p] * H[k * HS + p];
         }
-        __syncwarp();
-        const double d = H[k * HS + k];
-        __syncwarp();
+        if (i1 >= k && i1 < nU) {
+          acc1 = H[i1 * HS + k];
+          for (int p = 0; p < k; ++p) acc1 -= H[i1 * HS + p] * H[k * HS + p];
+        }
+        const double d = __shfl_sync(0xffffffffu, k < 32 ? acc0 : acc1, k & 31);
         if (!(d > 0.0)) { bad = true; break; }
-        const double ild = rsqrt(d);
-        NB_LL(i, nU) {
-          if (i > k) H[i * HS + k] *= ild;
-          else if (i == k) { H[i * HS + k] = d * ild; invd[k] = ild; }
-        }
+        const double ild = rsqrt64(d);
+        if (i0 == k) invd0 = ild;
+        if (i1 == k) invd1 = ild;
+        if (i0 >= k && i0 < nU) H[i0 * HS + k] = acc0 * ild;
+        if (i1 >= k && i1 < nU) H[i1 * HS + k] = acc1 * ild;
         __syncwarp();
       }
       if (bad) { stat |= 2; break; }
 
-      // predictor
-      NB_LL(k, m) cdz[k] = enabled(k) ? -cs[k] * cz[k] : 0.0;
-      __syncwarp();
-      newton();
-      const double a_aff = max_step();
-      double ga = 0.0;
-      NB_LL(k, m) if (enabled(k)) ga += (cs[k] + a_aff * cds[k]) * (cz[k] + a_aff * cdz[k]);
-      const double gap_aff = warp_sum(ga) / (double)(m_active > 0 ? m_active : 1);
-      const double sr = gap_aff / gap;
-      const double sigma = sr * sr * sr;
-      // corrector
-      NB_LL(k, m) cdz[k] = enabled(k) ? (-cs[k] * cz[k] + sigma * gap - cds[k] * cdz[k]) : 0.0;
-      __syncwarp();
-      newton();
-      double a = max_step();
-      a = fmin(1.0, 0.995 * a);
-      NB_LL(i, nU) x[i] += a * dU[i];
-      NB_LL(t, TD) Dv[t] += a * dD[t];
-      NB_LL(k, m) if (enabled(k)) { cs[k] += a * cds[k]; cz[k] += a * cdz[k]; }
+      // (e) predictor (pass 0) and corrector (pass 1) share one Newton body
+      NB_LL(k, mb) cdz[k] = enabled(k) ? -cs[k] * cz[k] : 0.0;
+#pragma unroll
+      for (int q_ = 0; q_ < HPL; ++q_) { hdzw[q_] = -hsw[q_] * hzw[q_]; hdzr[q_] = -hsr[q_] * hzr[q_]; }
+      double alpha = 1.0;
+      for (int pass = 0; pass < 2; ++pass) {
+        __syncwarp();
+        // hinge rows: b_w and y = (W_r/H_ww) b_w - v_r
+        double hbw[HPL];
+#pragma unroll
+        for (int q_ = 0; q_ < HPL; ++q_) {
+          const int k = lane + 32 * q_;
+          hbw[q_] = 0.0;
+          if (k < TM) {
+            const double vw = hdzw[q_] * (double)hisw[q_], vr = hdzr[q_] * (double)hisr[q_];
+            const double rdw = rho * hsw[q_] - hzw[q_] - hzr[q_];
+            hbw[q_] = -rdw + vw + vr;
+            const double wrh = hzr[q_] * (double)hisr[q_] * hih[q_];
+            tmpk[k] = wrh * hbw[q_] - vr;
+          }
+        }
+        __syncwarp();
+        NB_LL(t, TD) {
+          double Y0 = 0, Y1 = 0, Ys = 0;
+          for (int mm = 0; mm < M; ++mm) {
+            const int k = t * M + mm;
+            const double y = tmpk[k];
+            Y0 += y * (double)fax_s[k]; Y1 += y * (double)fay_s[k]; Ys += y;
+          }
+          const double vdu = cdz[oDU + t] * (double)cis[oDU + t], vdl = cdz[oDL + t] * (double)cis[oDL + t];
+          const double bb = -rdD[t] - (vdu - vdl) + Ys;
+          bD[t] = bb;
+          e0[t] = -Y0 + n0[t] * bb * iHDD[t];
+          e1[t] = -Y1 + n1[t] * bb * iHDD[t];
+        }
+        __syncwarp();
+        // right-hand side rows in registers, then L y = b, L^T x = y with shuffles
+        double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int i = lane + 32 * sl;
+          if (i < nU) {
+            double acc = -rdU[i] - (cdz[oBU + i] * (double)cis[oBU + i] - cdz[oBL + i] * (double)cis[oBL + i]);
+            if (i >= 2) acc -= cdz[oRU + i - 2] * (double)cis[oRU + i - 2] - cdz[oRL + i - 2] * (double)cis[oRL + i - 2];
+            if (i < nR) acc += cdz[oRU + i] * (double)cis[oRU + i] - cdz[oRL + i] * (double)cis[oRL + i];
+            if (TD > 0)
+              for (int t = i >> 1; t < T; ++t) acc += F[(0 * T + t) * nU + i] * e0[t] + F[(1 * T + t) * nU + i] * e1[t];
+            if (sl == 0) r0 = acc; else r1 = acc;
+          }
+        }
+        for (int k = 0; k < nU; ++k) {
+          const double mine = k < 32 ? r0 * invd0 : r1 * invd1;
+          const double yk = __shfl_sync(0xffffffffu, mine, k & 31);
+          if (lane == (k & 31)) { if (k < 32) r0 = yk; else r1 = yk; }
+          if (lane > k && lane < nU) r0 -= H[lane * HS + k] * yk;
+          if (lane + 32 > k && lane + 32 < nU) r1 -= H[(lane + 32) * HS + k] * yk;
+        }
+        for (int k = nU - 1; k >= 0; --k) {
+          const double mine = k < 32 ? r0 * invd0 : r1 * invd1;
+          const double xk = __shfl_sync(0xffffffffu, mine, k & 31);
+          if (lane == (k & 31)) { if (k < 32) r0 = xk; else r1 = xk; }
+          if (lane < k) r0 -= H[k * HS + lane] * xk;
+          if (lane + 32 < k) r1 -= H[k * HS + lane + 32] * xk;
+        }
+        if (lane < nU) dU[lane] = r0;
+        if (lane + 32 < nU) dU[lane + 32] = r1;
+        __syncwarp();
+        NB_LL(t, TD) {
+          double ax = 0, ay = 0;
+          for (int i = 0; i < 2 * (t + 1); ++i) {
+            ax += F[(0 * T + t) * nU + i] * dU[i];
+            ay += F[(1 * T + t) * nU + i] * dU[i];
+          }
+          qx[t] = ax; qy[t] = ay;
+          dD[t] = (bD[t] + n0[t] * ax + n1[t] * ay) * iHDD[t];
+        }
+        __syncwarp();
+        // steps of slacks / multipliers, and the largest relative decrease (for the step length)
+        float ratio = 0.f;
+#pragma unroll
+        for (int q_ = 0; q_ < HPL; ++q_) {
+          const int k = lane + 32 * q_;
+          if (k < TM) {
+            const int t = k / M;
+            const double Jdx = dD[t] - ((double)hfx[q_] * qx[t] + (double)hfy[q_] * qy[t]);
+            const double wrh = hzr[q_] * (double)hisr[q_] * hih[q_];
+            const double dw = hbw[q_] * hih[q_] + wrh * Jdx;
+            hdsw[q_] = dw; hdsr[q_] = dw - Jdx;
+            hdzw[q_] = (hdzw[q_] - hzw[q_] * hdsw[q_]) * (double)hisw[q_];
+            hdzr[q_] = (hdzr[q_] - hzr[q_] * hdsr[q_]) * (double)hisr[q_];
+            ratio = fmaxf(ratio, fmaxf(-(float)hdsw[q_] * hisw[q_], -(float)hdsr[q_] * hisr[q_]));
+            ratio = fmaxf(ratio, fmaxf(-(float)hdzw[q_] * rcpf(hzw[q_]), -(float)hdzr[q_] * rcpf(hzr[q_])));
+          }
+        }
+        NB_LL(i, nU) {
+          const double d = dU[i];
+          cdz[oBU + i] = (cdz[oBU + i] + cz[oBU + i] * d) * (double)cis[oBU + i]; cds[oBU + i] = -d;
+          cdz[oBL + i] = (cdz[oBL + i] - cz[oBL + i] * d) * (double)cis[oBL + i]; cds[oBL + i] = d;
+          if (i < nR) {
+            const double dd = dU[i + 2] - d;
+            cdz[oRU + i] = (cdz[oRU + i] + cz[oRU + i] * dd) * (double)cis[oRU + i]; cds[oRU + i] = -dd;
+            cdz[oRL + i] = (cdz[oRL + i] - cz[oRL + i] * dd) * (double)cis[oRL + i]; cds[oRL + i] = dd;
+          }
+        }
+        NB_LL(t, TD) {
+          const double d = dD[t];
+          cdz[oDU + t] = (cdz[oDU + t] + cz[oDU + t] * d) * (double)cis[oDU + t]; cds[oDU + t] = -d;
+          cdz[oDL + t] = (cdz[oDL + t] - cz[oDL + t] * d) * (double)cis[oDL + t]; cds[oDL + t] = d;
+        }
+        __syncwarp();
+        NB_LL(k, mb) {
+          if (!enabled(k)) continue;
+          ratio = fmaxf(ratio, fmaxf(-(float)cds[k] * cis[k], -(float)cdz[k] * rcpf(cz[k])));
+        }
+        ratio = warp_maxf(ratio);
+        if (pass == 0) {
+          const double amax = ratio > 1.0f ? 1.0 / (double)ratio : 1.0;  // largest step <= 1 keeping s, z >= 0
+          double ga = 0.0;
+          NB_LL(k, mb) if (enabled(k)) ga += (cs[k] + amax * cds[k]) * (cz[k] + amax * cdz[k]);
+#pragma unroll
+          for (int q_ = 0; q_ < HPL; ++q_)
+            if (lane + 32 * q_ < TM)
+              ga += (hsw[q_] + amax * hdsw[q_]) * (hzw[q_] + amax * hdzw[q_]) + (hsr[q_] + amax * hdsr[q_]) * (hzr[q_] + amax * hdzr[q_]);
+          const double sr = fmax(warp_sum(ga) * inv_m, 0.0) / gap;
+          const double smu = sr * sr * sr * gap;  // sigma * mu
+          NB_LL(k, mb) cdz[k] = enabled(k) ? (-cs[k] * cz[k] + smu - cds[k] * cdz[k]) : 0.0;
+#pragma unroll
+          for (int q_ = 0; q_ < HPL; ++q_) {
+            hdzw[q_] = -hsw[q_] * hzw[q_] + smu - hdsw[q_] * hdzw[q_];
+            hdzr[q_] = -hsr[q_] * hzr[q_] + smu - hdsr[q_] * hdzr[q_];
+          }
+        } else {
+          alpha = ratio > 0.995f ? 0.995 / (double)ratio : 1.0;
+        }
+      }
+      NB_LL(i, nU) x[i] += alpha * dU[i];
+      NB_LL(t, TD) Dv[t] += alpha * dD[t];
+      NB_LL(k, mb) if (enabled(k)) { cs[k] += alpha * cds[k]; cz[k] += alpha * cdz[k]; }
+#pragma unroll
+      for (int q_ = 0; q_ < HPL; ++q_) {
+        if (lane + 32 * q_ < TM) {
+          hsw[q_] += alpha * hdsw[q_]; hsr[q_] += alpha * hdsr[q_];
+          hzw[q_] += alpha * hdzw[q_]; hzr[q_] += alpha * hdzr[q_];
+        }
+      }
       __syncwarp();
     }
     if (!converged && !(stat & 2)) stat |= 1;
@@ -551,20 +634,21 @@ __global__ void __launch_bounds__(256) nrmp_kernel(const NrmpParams prm, int war
       sx += F[(0 * T + t) * nU + i] * x[i]; sy += F[(1 * T + t) * nU + i] * x[i]; sth += F[(2 * T + t) * nU + i] * x[i];
     }
     if (keep_nominal) { sx = ns[t + 1]; sy = ns[T1 + t + 1]; sth = ns[2 * T1 + t + 1]; }
-    // stash in Gx (no longer needed) so that reads of nom_s above are complete before any write
-    Gx[3 * t] = sx; Gx[3 * t + 1] = sy; Gx[3 * t + 2] = sth;
+    // stash (H is dead) so that every read of nom_s is complete before any write (out may alias nom)
+    H[3 * t] = sx; H[3 * t + 1] = sy; H[3 * t + 2] = sth;
   }
-  NB_LL(i, nU) Gy[i] = keep_nominal ? (double)nu[(i & 1) * T + (i >> 1)] : x[i];
+  NB_LL(i, nU) rdU[i] = keep_nominal ? (double)nu[(i & 1) * T + (i >> 1)] : x[i];
   __syncwarp();
   if (lane < 3) os[lane * T1] = init_s;
   NB_LL(t, T) {
-    os[t + 1] = (float)Gx[3 * t]; os[T1 + t + 1] = (float)Gx[3 * t + 1]; os[2 * T1 + t + 1] = (float)Gx[3 * t + 2];
+    os[t + 1] = (float)H[3 * t]; os[T1 + t + 1] = (float)H[3 * t + 1]; os[2 * T1 + t + 1] = (float)H[3 * t + 2];
     od[t] = TD > 0 ? (float)Dv[t] : 0.f;
   }
-  NB_LL(i, nU) ou[(i & 1) * T + (i >> 1)] = (float)Gy[i];
+  NB_LL(i, nU) ou[(i & 1) * T + (i >> 1)] = (float)rdU[i];
   if (lane == 0) {
     if (prm.status) prm.status[b] = stat;
     if (prm.iters) prm.iters[b] += 1;
+    if (prm.ipm_iters) prm.ipm_iters[b] = it;
   }
   __syncwarp();
 

@@ -58,7 +58,7 @@ struct nb_pan {
   float *sel_mu = nullptr, *sel_lam = nullptr, *sel_pts = nullptr, *sel_dist = nullptr;
   int32_t* sel_count = nullptr;
   float *prev_s = nullptr, *prev_u = nullptr, *prev_mu = nullptr, *prev_lam = nullptr;
-  int32_t *prev_count = nullptr, *prev_valid = nullptr, *active = nullptr, *iters = nullptr, *status = nullptr;
+  int32_t *prev_count = nullptr, *prev_valid = nullptr, *active = nullptr, *iters = nullptr, *status = nullptr, *ipm_it = nullptr;
   float* min_dist = nullptr;
   // staging for the host-pointer entry point
   float *h_in = nullptr, *h_out = nullptr;  // device staging
@@ -140,21 +140,28 @@ int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st) {
   }
   for (int e = 0; e < nb::kMaxEdges; ++e) prm.h[e] = p->geo.h[e];
   const size_t wd = nb::nrmp_warp_doubles(prm.T, prm.M);
-  int warps = (int)((size_t)p->max_smem_optin / (wd * sizeof(double)));
+  const size_t extra = nb::nrmp_cta_extra_bytes(prm.T);
+  const int TM = prm.T * prm.M;
+  if (TM > 256) return fail(NB_ERR_CAPACITY, "receding*nrmp_max_num = %d exceeds 256", TM);
+  int warps = (int)(((size_t)p->max_smem_optin - extra) / (wd * sizeof(double)));
   if (warps < 1) return fail(NB_ERR_CAPACITY, "T=%d, M=%d need %zu B of shared memory per environment", prm.T, prm.M, wd * 8);
-  // two CTAs per SM when possible so that one CTA's tail overlaps the other's work
-  if (warps >= 4) warps = warps / 2;
-  if (warps > 8) warps = 8;
-  const size_t smem = (size_t)warps * wd * sizeof(double);
-  if (!p->nrmp_attr_set) {
-    NB_CUDA(cudaFuncSetAttribute(nb::nrmp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem_optin));
-    p->nrmp_attr_set = true;
-  }
+  // small CTAs (<= 2 warps): many of them fit per SM and each warp retires independently
+  if (warps > 2) warps = 2;
+  const size_t smem = (size_t)warps * wd * sizeof(double) + extra;
   const int grid = (prm.B + warps - 1) / warps;
-  nb::nrmp_kernel<<<grid, warps * 32, smem, st>>>(prm, warps, (int)wd);
-  ++g_launches;
-  NB_CUDA(cudaGetLastError());
-  return NB_OK;
+  auto go = [&](auto kern) -> int {
+    NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem_optin));
+    kern<<<grid, warps * 32, smem, st>>>(prm, warps, (int)wd);
+    ++g_launches;
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+  };
+  const int hpl = (TM + 31) / 32;
+  if (hpl <= 1) return go(nb::nrmp_kernel<1>);
+  if (hpl <= 2) return go(nb::nrmp_kernel<2>);
+  if (hpl <= 4) return go(nb::nrmp_kernel<4>);
+  if (hpl <= 5) return go(nb::nrmp_kernel<5>);
+  return go(nb::nrmp_kernel<8>);
 }
 
 __global__ void init_run_kernel(int B, int32_t* active, int32_t* iters, int32_t* status, float* min_dist, int32_t* sel_count) {
@@ -240,6 +247,8 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
   NB_CUDA(dalloc(&p->active, B));
   NB_CUDA(dalloc(&p->iters, B));
   NB_CUDA(dalloc(&p->status, B));
+  NB_CUDA(dalloc(&p->ipm_it, B));
+  NB_CUDA(cudaMemset(p->ipm_it, 0, B * sizeof(int32_t)));
   NB_CUDA(dalloc(&p->min_dist, B));
   NB_CUDA(cudaMemset(p->prev_valid, 0, B * sizeof(int32_t)));
   NB_CUDA(cudaMemset(p->prev_count, 0, B * sizeof(int32_t)));
@@ -252,7 +261,7 @@ int nb_pan_destroy(nb_pan_t* p) {
   if (!p) return NB_OK;
   cudaSetDevice(p->cfg.device);
   void* bufs[] = {p->d_image, p->d_weights, p->sel_mu, p->sel_lam, p->sel_pts, p->sel_dist, p->sel_count, p->prev_s, p->prev_u, p->prev_mu,
-                  p->prev_lam, p->prev_count, p->prev_valid, p->active, p->iters, p->status, p->min_dist, p->h_in, p->h_out, p->h_np, p->h_io};
+                  p->prev_lam, p->prev_count, p->prev_valid, p->active, p->iters, p->status, p->ipm_it, p->min_dist, p->h_in, p->h_out, p->h_np, p->h_io};
   for (void* b : bufs)
     if (b) cudaFree(b);
   delete p;
@@ -351,6 +360,7 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
     n.nom_s = out_s; n.nom_u = out_u; n.ref_s = ref_s; n.ref_us = ref_us;
     if (with_dune) { n.sel_mu = p->sel_mu; n.sel_lam = p->sel_lam; n.sel_pts = p->sel_pts; n.sel_count = p->sel_count; }
     n.out_s = out_s; n.out_u = out_u; n.out_d = out_d; n.status = p->status; n.iters = p->iters; n.active = p->active;
+    n.ipm_iters = p->ipm_it;
     n.prev_s = p->prev_s; n.prev_u = p->prev_u; n.prev_mu = p->prev_mu; n.prev_lam = p->prev_lam;
     n.prev_count = p->prev_count; n.prev_valid = p->prev_valid;
     n.B = B;
@@ -373,6 +383,13 @@ int nb_pan_read_selection(nb_pan_t* p, int32_t B, float* sel_mu, float* sel_lam,
   if (sel_points) NB_CUDA(cudaMemcpyAsync(sel_points, p->sel_pts, (size_t)B * T1 * M * 2 * 4, cudaMemcpyDeviceToDevice, st));
   if (sel_distance) NB_CUDA(cudaMemcpyAsync(sel_distance, p->sel_dist, (size_t)B * T1 * M * 4, cudaMemcpyDeviceToDevice, st));
   if (sel_count) NB_CUDA(cudaMemcpyAsync(sel_count, p->sel_count, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  return NB_OK;
+}
+
+int nb_pan_read_diagnostics(nb_pan_t* p, int32_t B, int32_t* ipm_iterations, void* stream) {
+  if (int rc = check_forward_args(p, B, 0)) return rc;
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  if (ipm_iterations) NB_CUDA(cudaMemcpyAsync(ipm_iterations, p->ipm_it, (size_t)B * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return NB_OK;
 }
 
