@@ -76,6 +76,7 @@ __host__ __device__ inline size_t nrmp_warp_doubles(int T, int M) {
   n += 4 * (size_t)mb;             // s, z, ds, dz of the box / rate / D rows
   n += ((size_t)mb + 1) / 2;       // is (float)
   n += (size_t)TM;                 // fax, fay (float)
+  n += ((size_t)mb + 1) / 2;       // row-enable flags (float)
   return n + 4;
 }
 __host__ __device__ inline size_t nrmp_cta_extra_bytes(int T) {  // pair table (uint16) shared by the CTA's warps
@@ -83,7 +84,7 @@ __host__ __device__ inline size_t nrmp_cta_extra_bytes(int T) {  // pair table (
   return (((size_t)nU * (nU + 1) / 2) * 2 + 15) / 16 * 16;
 }
 
-#define NB_LL(i, n) for (int i = lane; i < (n); i += 32)
+#define NB_LL(i, n) _Pragma("unroll 1") for (int i = lane; i < (n); i += 32)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -115,9 +116,15 @@ __device__ __forceinline__ double rsqrt64(double x) {
   for (int i = 0; i < 3; ++i) r = r * fma(-0.5 * x, r * r, 1.5);
   return r;
 }
-__device__ __forceinline__ float rcpf(double x) { return __frcp_rn((float)x); }
+__device__ __forceinline__ float rcpf(double x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)x));
+  return r;
+}
 
-template <int HPL>
+// SMALL: 2T <= 32, every lane owns at most one row of the reduced system (one register slot in the
+// triangular solves); the general version (T <= 32) carries a second slot.
+template <int HPL, bool SMALL>
 __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpParams prm, int warps_per_cta, int warp_doubles) {
   extern __shared__ __align__(16) double smem_d[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -176,6 +183,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
   float* cis = reinterpret_cast<float*>(wsp);  wsp += (mb + 1) / 2;  // inverse slacks
   float* fax_s = reinterpret_cast<float*>(wsp);
   float* fay_s = fax_s + TM;
+  float* cen = fay_s + TM;  // 1.0 for rows whose bound is finite, else 0.0
   // setup-only linearisation data lives in the scratch region
   double* a02 = scratch;      double* a12 = scratch + T;  double* Bm = scratch + 2 * T;  double* Cm = scratch + 8 * T;
   double* gam_b = scratch + 11 * T;
@@ -188,11 +196,13 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
   const int rows_s = omni ? 2 : 3;
   const bool en_speed[2] = {isfinite(prm.speed[0]), isfinite(prm.speed[1])};
   const bool en_acce[2] = {isfinite(prm.acce[0]), isfinite(prm.acce[1])};
-  auto enabled = [&](int k) -> bool {  // rows of the shared-memory constraint block
-    if (k < oRU) return en_speed[(k % nU) & 1];
-    if (k < oDU) return en_acce[((k - oRU) % nR) & 1];
-    return true;
-  };
+  NB_LL(k, mb) {  // rows of the shared-memory constraint block that are switched on
+    bool on = true;
+    if (k < oRU) on = en_speed[(k % nU) & 1];
+    else if (k < oDU) on = en_acce[((k - oRU) % nR) & 1];
+    cen[k] = on ? 1.0f : 0.0f;
+  }
+  auto enabled = [&](int k) -> bool { return cen[k] != 0.0f; };
   int m_active = 2 * TD + 2 * TM;
   for (int c = 0; c < 2; ++c) m_active += (en_speed[c] ? 2 * T : 0) + (en_acce[c] ? 2 * (T - 1) : 0);
   const double inv_m = 1.0 / (double)(m_active > 0 ? m_active : 1);
@@ -288,14 +298,16 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
   float hfx[HPL], hfy[HPL];
   double hsw[HPL], hsr[HPL], hzw[HPL], hzr[HPL], hdsw[HPL], hdsr[HPL], hdzw[HPL], hdzr[HPL];
   float hisw[HPL], hisr[HPL];
+  int hts[HPL];  // horizon step of each owned hinge row
   double hih[HPL];  // 1/H_ww must be FP64: the slack elimination has to be exact for the Newton system to stay consistent
 #pragma unroll
   for (int q_ = 0; q_ < HPL; ++q_) {
     const int k = lane + 32 * q_;
-    hfx[q_] = 0.f; hfy[q_] = 0.f; hsw[q_] = 1.0; hsr[q_] = 1.0; hzw[q_] = 0.0; hzr[q_] = 0.0;
+    hts[q_] = 0; hfx[q_] = 0.f; hfy[q_] = 0.f; hsw[q_] = 1.0; hsr[q_] = 1.0; hzw[q_] = 0.0; hzr[q_] = 0.0;
     hdsw[q_] = hdsr[q_] = hdzw[q_] = hdzr[q_] = 0.0; hisw[q_] = hisr[q_] = 0.f; hih[q_] = 0.0;
     if (k < TM) {
       const int t = k / M, mm = k - t * M;
+      hts[q_] = t;
       float fx = 0.f, fy = 0.f, fbv = 0.f;
       if (prm.fa) {
         fx = prm.fa[((size_t)b * TM + k) * 2]; fy = prm.fa[((size_t)b * TM + k) * 2 + 1]; fbv = prm.fb[(size_t)b * TM + k];
@@ -345,6 +357,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
   int it = 0;
   bool converged = false;
   if (stat == 0) {
+#pragma unroll 1
     for (it = 0; it < prm.max_ipm_iter; ++it) {
       // (a) dual residual, gap
 #pragma unroll
@@ -367,15 +380,23 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
       double res = 0.0, gsum = 0.0;
       NB_LL(i, nU) {
         double acc = cv[i];
-        for (int j = 0; j < nU; ++j) {
-          const int hi = i > j ? i : j, lo = i > j ? j : i;
-          acc += Hc[hi * (hi + 1) / 2 + lo] * x[j];
+        {
+          const double* hp = Hc + i * (i + 1) / 2;  // row i of the packed lower triangle, then column i below the diagonal
+#pragma unroll 2
+          for (int j = 0; j <= i; ++j) acc += hp[j] * x[j];
+          hp += i + i + 1;  // element (i+1, i)
+#pragma unroll 2
+          for (int j = i + 1; j < nU; ++j) { acc += *hp * x[j]; hp += j + 1; }
         }
         acc += cz[oBU + i] - cz[oBL + i];
         if (i >= 2) acc += cz[oRU + i - 2] - cz[oRL + i - 2];
         if (i < nR) acc -= cz[oRU + i] - cz[oRL + i];
-        if (TD > 0)
-          for (int t = i >> 1; t < T; ++t) acc -= F[(0 * T + t) * nU + i] * e0[t] + F[(1 * T + t) * nU + i] * e1[t];
+        if (TD > 0) {
+          const double* fxp = F + (i >> 1) * nU + i;
+          const double* fyp = fxp + T * nU;
+#pragma unroll 2
+          for (int t = i >> 1; t < T; ++t, fxp += nU, fyp += nU) acc -= fxp[0] * e0[t] + fyp[0] * e1[t];
+        }
         rdU[i] = acc;
         res = fmax(res, fabs(acc));
       }
@@ -422,20 +443,32 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
       }
       __syncwarp();
       if (TD > 0) {
-        NB_LL(j, nU)
-          for (int t = j >> 1; t < T; ++t) {
-            const double fx = F[(0 * T + t) * nU + j], fy = F[(1 * T + t) * nU + j];
-            Gx[t * nU + j] = N00[t] * fx + N01[t] * fy;
-            Gy[t * nU + j] = N01[t] * fx + N11[t] * fy;
+        NB_LL(j, nU) {
+          const double* fxp = F + (j >> 1) * nU + j;
+          const double* fyp = fxp + T * nU;
+          double* gxp = Gx + (j >> 1) * nU + j;
+          double* gyp = gxp + T * nU;
+#pragma unroll 2
+          for (int t = j >> 1; t < T; ++t, fxp += nU, fyp += nU, gxp += nU, gyp += nU) {
+            const double fx = fxp[0], fy = fyp[0];
+            gxp[0] = N00[t] * fx + N01[t] * fy;
+            gyp[0] = N01[t] * fx + N11[t] * fy;
           }
+        }
         __syncwarp();
       }
       // (c) reduced Hessian, lower triangle
       NB_LL(p, nP) {
         const int i = ptab[p] >> 8, j = ptab[p] & 255;
         double acc = Hc[p];
-        if (TD > 0)
-          for (int t = i >> 1; t < T; ++t) acc += F[(0 * T + t) * nU + i] * Gx[t * nU + j] + F[(1 * T + t) * nU + i] * Gy[t * nU + j];
+        if (TD > 0) {
+          const double* fxp = F + (i >> 1) * nU + i;
+          const double* fyp = fxp + T * nU;
+          const double* gxp = Gx + (i >> 1) * nU + j;
+          const double* gyp = gxp + T * nU;
+#pragma unroll 2
+          for (int t = i >> 1; t < T; ++t, fxp += nU, fyp += nU, gxp += nU, gyp += nU) acc += fxp[0] * gxp[0] + fyp[0] * gyp[0];
+        }
         if (i == j) {
           acc += cz[oBU + i] * (double)cis[oBU + i] + cz[oBL + i] * (double)cis[oBL + i];
           if (i >= 2) acc += cz[oRU + i - 2] * (double)cis[oRU + i - 2] + cz[oRL + i - 2] * (double)cis[oRL + i - 2];
@@ -449,24 +482,30 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
       // (d) Cholesky, left-looking by column; lane owns rows lane, lane+32; inverse diagonal in registers
       bool bad = false;
       double invd0 = 0.0, invd1 = 0.0;
+#pragma unroll 1
       for (int k = 0; k < nU; ++k) {
         double acc0 = 0.0, acc1 = 0.0;
         const int i0 = lane, i1 = lane + 32;
+        const double* rowk = H + k * HS;
         if (i0 >= k && i0 < nU) {
-          acc0 = H[i0 * HS + k];
-          for (int p = 0; p < k; ++p) acc0 -= H[i0 * HS + p] * H[k * HS + p];
+          const double* rowi = H + i0 * HS;
+          acc0 = rowi[k];
+#pragma unroll 4
+          for (int p = 0; p < k; ++p) acc0 -= rowi[p] * rowk[p];
         }
-        if (i1 >= k && i1 < nU) {
-          acc1 = H[i1 * HS + k];
-          for (int p = 0; p < k; ++p) acc1 -= H[i1 * HS + p] * H[k * HS + p];
+        if (!SMALL && i1 >= k && i1 < nU) {
+          const double* rowi = H + i1 * HS;
+          acc1 = rowi[k];
+#pragma unroll 4
+          for (int p = 0; p < k; ++p) acc1 -= rowi[p] * rowk[p];
         }
-        const double d = __shfl_sync(0xffffffffu, k < 32 ? acc0 : acc1, k & 31);
+        const double d = __shfl_sync(0xffffffffu, (SMALL || k < 32) ? acc0 : acc1, k & 31);
         if (!(d > 0.0)) { bad = true; break; }
         const double ild = rsqrt64(d);
         if (i0 == k) invd0 = ild;
-        if (i1 == k) invd1 = ild;
+        if (!SMALL && i1 == k) invd1 = ild;
         if (i0 >= k && i0 < nU) H[i0 * HS + k] = acc0 * ild;
-        if (i1 >= k && i1 < nU) H[i1 * HS + k] = acc1 * ild;
+        if (!SMALL && i1 >= k && i1 < nU) H[i1 * HS + k] = acc1 * ild;
         __syncwarp();
       }
       if (bad) { stat |= 2; break; }
@@ -476,6 +515,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
 #pragma unroll
       for (int q_ = 0; q_ < HPL; ++q_) { hdzw[q_] = -hsw[q_] * hzw[q_]; hdzr[q_] = -hsr[q_] * hzr[q_]; }
       double alpha = 1.0;
+#pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
         __syncwarp();
         // hinge rows: b_w and y = (W_r/H_ww) b_w - v_r
@@ -510,39 +550,65 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
         // right-hand side rows in registers, then L y = b, L^T x = y with shuffles
         double r0 = 0.0, r1 = 0.0;
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
+        for (int sl = 0; sl < (SMALL ? 1 : 2); ++sl) {
           const int i = lane + 32 * sl;
           if (i < nU) {
             double acc = -rdU[i] - (cdz[oBU + i] * (double)cis[oBU + i] - cdz[oBL + i] * (double)cis[oBL + i]);
             if (i >= 2) acc -= cdz[oRU + i - 2] * (double)cis[oRU + i - 2] - cdz[oRL + i - 2] * (double)cis[oRL + i - 2];
             if (i < nR) acc += cdz[oRU + i] * (double)cis[oRU + i] - cdz[oRL + i] * (double)cis[oRL + i];
-            if (TD > 0)
-              for (int t = i >> 1; t < T; ++t) acc += F[(0 * T + t) * nU + i] * e0[t] + F[(1 * T + t) * nU + i] * e1[t];
+            if (TD > 0) {
+              const double* fxp = F + (i >> 1) * nU + i;
+              const double* fyp = fxp + T * nU;
+#pragma unroll 2
+              for (int t = i >> 1; t < T; ++t, fxp += nU, fyp += nU) acc += fxp[0] * e0[t] + fyp[0] * e1[t];
+            }
             if (sl == 0) r0 = acc; else r1 = acc;
           }
         }
-        for (int k = 0; k < nU; ++k) {
-          const double mine = k < 32 ? r0 * invd0 : r1 * invd1;
-          const double yk = __shfl_sync(0xffffffffu, mine, k & 31);
-          if (lane == (k & 31)) { if (k < 32) r0 = yk; else r1 = yk; }
-          if (lane > k && lane < nU) r0 -= H[lane * HS + k] * yk;
-          if (lane + 32 > k && lane + 32 < nU) r1 -= H[(lane + 32) * HS + k] * yk;
-        }
-        for (int k = nU - 1; k >= 0; --k) {
-          const double mine = k < 32 ? r0 * invd0 : r1 * invd1;
-          const double xk = __shfl_sync(0xffffffffu, mine, k & 31);
-          if (lane == (k & 31)) { if (k < 32) r0 = xk; else r1 = xk; }
-          if (lane < k) r0 -= H[k * HS + lane] * xk;
-          if (lane + 32 < k) r1 -= H[k * HS + lane + 32] * xk;
+        if (SMALL) {
+          const double* rowl = H + lane * HS;  // L[lane][k], k < lane
+#pragma unroll 2
+          for (int k = 0; k < nU; ++k) {
+            const double yk = __shfl_sync(0xffffffffu, r0 * invd0, k);
+            if (lane == k) r0 = yk;
+            if (lane > k && lane < nU) r0 -= rowl[k] * yk;
+          }
+          const double* coll = H + lane;  // L[k][lane], k > lane
+#pragma unroll 2
+          for (int k = nU - 1; k >= 0; --k) {
+            const double xk = __shfl_sync(0xffffffffu, r0 * invd0, k);
+            if (lane == k) r0 = xk;
+            if (lane < k) r0 -= coll[k * HS] * xk;
+          }
+        } else {
+#pragma unroll 1
+          for (int k = 0; k < nU; ++k) {
+            const double mine = k < 32 ? r0 * invd0 : r1 * invd1;
+            const double yk = __shfl_sync(0xffffffffu, mine, k & 31);
+            if (lane == (k & 31)) { if (k < 32) r0 = yk; else r1 = yk; }
+            if (lane > k && lane < nU) r0 -= H[lane * HS + k] * yk;
+            if (lane + 32 > k && lane + 32 < nU) r1 -= H[(lane + 32) * HS + k] * yk;
+          }
+#pragma unroll 1
+          for (int k = nU - 1; k >= 0; --k) {
+            const double mine = k < 32 ? r0 * invd0 : r1 * invd1;
+            const double xk = __shfl_sync(0xffffffffu, mine, k & 31);
+            if (lane == (k & 31)) { if (k < 32) r0 = xk; else r1 = xk; }
+            if (lane < k) r0 -= H[k * HS + lane] * xk;
+            if (lane + 32 < k) r1 -= H[k * HS + lane + 32] * xk;
+          }
         }
         if (lane < nU) dU[lane] = r0;
-        if (lane + 32 < nU) dU[lane + 32] = r1;
+        if (!SMALL && lane + 32 < nU) dU[lane + 32] = r1;
         __syncwarp();
         NB_LL(t, TD) {
           double ax = 0, ay = 0;
+          const double* fxp = F + t * nU;
+          const double* fyp = fxp + T * nU;
+#pragma unroll 2
           for (int i = 0; i < 2 * (t + 1); ++i) {
-            ax += F[(0 * T + t) * nU + i] * dU[i];
-            ay += F[(1 * T + t) * nU + i] * dU[i];
+            ax += fxp[i] * dU[i];
+            ay += fyp[i] * dU[i];
           }
           qx[t] = ax; qy[t] = ay;
           dD[t] = (bD[t] + n0[t] * ax + n1[t] * ay) * iHDD[t];
@@ -554,7 +620,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
         for (int q_ = 0; q_ < HPL; ++q_) {
           const int k = lane + 32 * q_;
           if (k < TM) {
-            const int t = k / M;
+            const int t = hts[q_];
             const double Jdx = dD[t] - ((double)hfx[q_] * qx[t] + (double)hfy[q_] * qy[t]);
             const double wrh = hzr[q_] * (double)hisr[q_] * hih[q_];
             const double dw = hbw[q_] * hih[q_] + wrh * Jdx;

@@ -92,3 +92,22 @@ def test_oracle_pan_trace_regression(cname, scene):
         assert np.abs(S - z["S"][0, k]).max() < 2e-5 and np.abs(U - z["U"][0, k]).max() < 2e-5
         assert np.abs(D - z["D"][0, k]).max() < 2e-5 and abs(pan.min_distance - z["min_distance"][0, k]) < 1e-6
         s, u = z["S"][0, k], z["U"][0, k]
+
+
+def test_oracle_iteration_amplifies_perturbations():
+    """Documents why end-to-end K-iteration parity can only be statistical: ONE oracle PAN iteration
+    maps a 1e-6 relative perturbation of its nominal input to a >10x larger change of its output in
+    cluttered / acker scenes (re-linearisation + penalty rho = 400), independent of any GPU code."""
+    cfg = CONFIGS["C2"]
+    inp = make_inputs(cfg, B=8, scene="obstacles")
+    amp = []
+    for b in range(8):
+        vel = inp["velocities"][b]
+        first = oracle_factory(cfg, K=1)()
+        s1, u1, _ = first.forward(inp["nom_s"][b], inp["nom_u"][b], inp["ref_s"][b], inp["ref_us"][b], inp["points"][b], vel)
+        base = oracle_factory(cfg, K=1)().forward(s1, u1, inp["ref_s"][b], inp["ref_us"][b], inp["points"][b], vel)
+        rng = np.random.default_rng(b)
+        du = (1e-6 * np.abs(u1).max() * rng.standard_normal(u1.shape)).astype(np.float32)
+        pert = oracle_factory(cfg, K=1)().forward(s1, u1 + du, inp["ref_s"][b], inp["ref_us"][b], inp["points"][b], vel)
+        amp.append(np.abs(pert[1] - base[1]).max() / np.abs(du).max())
+    assert max(amp) > 5.0, amp
