@@ -41,16 +41,20 @@ void build_mma_image(const float* w, int E, std::vector<unsigned char>& out) {
   for (int l = 0; l < 4; ++l) emit(frag + (size_t)l * I::kHiddenFragU4 * 4, w + hidden_off[l], 32, 4);
   emit(frag + (size_t)4 * I::kHiddenFragU4 * 4, w + L::W13, E, 1);
   auto cp = [&](int dst, int src, int n) { memcpy(fl + dst, w + src, (size_t)n * 4); };
-  cp(I::W0, L::W0, 64); cp(I::B0, L::B0, 32); cp(I::G1, L::G1, 32); cp(I::BE1, L::BE1, 32);
-  cp(I::B3, L::B3, 32); cp(I::B5, L::B5, 32); cp(I::G6, L::G6, 32); cp(I::BE6, L::BE6, 32);
-  cp(I::B8, L::B8, 32); cp(I::B10, L::B10, 32); cp(I::G11, L::G11, 32); cp(I::BE11, L::BE11, 32);
+  // LayerNorm gain / offset pre-multiplied by 2*log2(e): tanh(y) = 1 - 2/(exp2(2*log2(e)*y) + 1)
+  auto cps = [&](int dst, int src, int n) {
+    for (int i = 0; i < n; ++i) fl[dst + i] = (float)((double)w[src + i] * 2.8853900817779268);
+  };
+  cp(I::W0, L::W0, 64); cp(I::B0, L::B0, 32); cps(I::G1, L::G1, 32); cps(I::BE1, L::BE1, 32);
+  cp(I::B3, L::B3, 32); cp(I::B5, L::B5, 32); cps(I::G6, L::G6, 32); cps(I::BE6, L::BE6, 32);
+  cp(I::B8, L::B8, 32); cp(I::B10, L::B10, 32); cps(I::G11, L::G11, 32); cps(I::BE11, L::BE11, 32);
   cp(I::B13, L::b13(E), E);
 }
 
 int launch_dune_mma(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, cudaStream_t st, char* err,
                     size_t errlen) {
   const int N = prm.N, E = prm.geo.E;
-  const size_t smem = dune_mma_smem_bytes(N, E);
+  const size_t smem = dune_mma_smem_bytes(N, E, prm.M);
   if ((long long)smem > max_smem_optin) {
     snprintf(err, errlen, "N=%d needs %zu B of shared memory (limit %d)", N, smem, max_smem_optin);
     return -3;

@@ -27,7 +27,8 @@ namespace nb {
 // Fragment-ordered weight image built on the host (pan_api.cu: build_mma_image):
 //   for each hidden layer L in {3,5,8,10}: uint4 frag[2 ksteps][4 ntiles][32 lanes] = {b0_hi, b1_hi, b0_lo, b1_lo}
 //   last layer (13, N padded to 8):        uint4 frag[2 ksteps][1 ntile][32 lanes]
-//   then the fp32 vectors: W0 (32x2), b0, g1, be1, b3, b5, g6, be6, b8, b10, g11, be11, b13 (8, zero padded)
+//   then the fp32 vectors: W0 (32x2), b0, g1, be1, b3, b5, g6, be6, b8, b10, g11, be11, b13 (8, zero padded);
+//   the LayerNorm gains / offsets g*, be* are stored pre-multiplied by 2*log2(e) (tanh via exp2)
 struct MmaImage {
   static constexpr int kHiddenFragU4 = 2 * 4 * 32;  // uint4 per hidden layer
   static constexpr int kLastFragU4 = 2 * 1 * 32;
@@ -52,9 +53,9 @@ __device__ __forceinline__ void split_pack(float v0, float v1, uint32_t& hi, uin
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-__device__ __forceinline__ float tanh_fast(float x) {
+// tanh(x) given a = 2*log2(e)*x (the LayerNorm affine is pre-scaled by that constant in the weight image)
+__device__ __forceinline__ float tanh_scaled(float a) {
   float e, r;
-  const float a = x * 2.8853900817779268f;  // 2*log2(e)
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
   const float d = e + 1.0f;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
@@ -129,10 +130,10 @@ __device__ __forceinline__ void ln_tanh_tile(float (&acc)[4][4], const float* __
   for (int j = 0; j < 4; ++j) {
     const float2 gg = *reinterpret_cast<const float2*>(g + 8 * j + t2);
     const float2 bb = *reinterpret_cast<const float2*>(be + 8 * j + t2);
-    acc[j][0] = tanh_fast(fmaf(acc[j][0] * r0, gg.x, bb.x));
-    acc[j][1] = tanh_fast(fmaf(acc[j][1] * r0, gg.y, bb.y));
-    acc[j][2] = tanh_fast(fmaf(acc[j][2] * r1, gg.x, bb.x));
-    acc[j][3] = tanh_fast(fmaf(acc[j][3] * r1, gg.y, bb.y));
+    acc[j][0] = tanh_scaled(fmaf(acc[j][0] * r0, gg.x, bb.x));
+    acc[j][1] = tanh_scaled(fmaf(acc[j][1] * r0, gg.y, bb.y));
+    acc[j][2] = tanh_scaled(fmaf(acc[j][2] * r1, gg.x, bb.x));
+    acc[j][3] = tanh_scaled(fmaf(acc[j][3] * r1, gg.y, bb.y));
   }
 }
 
@@ -145,8 +146,8 @@ __device__ __forceinline__ void relu_tile(float (&acc)[4][4]) {
 
 constexpr int kMT = 2;  // 16-row tiles per warp pass: 32 points
 
-__host__ __device__ inline size_t dune_mma_smem_bytes(int N, int E) {
-  return MmaImage::kBytes + (size_t)N * 8 + (size_t)N * E * 4 + 16;
+__host__ __device__ inline size_t dune_mma_smem_bytes(int N, int E, int M) {
+  return MmaImage::kBytes + (size_t)N * 8 + (((size_t)N * E * 4 + 7) / 8) * 8 + (size_t)kDuneMaxWarps * M * 8 + 16;
 }
 
 __global__ void __launch_bounds__(256, 2) dune_mma_kernel(const DuneParams prm, const unsigned char* __restrict__ image) {
@@ -156,8 +157,7 @@ __global__ void __launch_bounds__(256, 2) dune_mma_kernel(const DuneParams prm, 
   const float* fl = reinterpret_cast<const float*>(smem_raw + (size_t)I::kFragU4 * 16);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + I::kBytes);
   float* smu = reinterpret_cast<float*>(smem_raw + I::kBytes + (size_t)prm.N * 8);
-  __shared__ unsigned long long warp_min[2][kDuneMaxWarps];
-
+  unsigned long long* cands = reinterpret_cast<unsigned long long*>(smem_raw + I::kBytes + (size_t)prm.N * 8 + (((size_t)prm.N * prm.geo.E * 4 + 7) / 8) * 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int g = lane >> 2, t2 = (lane & 3) * 2;
   for (int i = tid; i < (int)(I::kBytes / 16); i += nthreads) reinterpret_cast<uint4*>(smem_raw)[i] = reinterpret_cast<const uint4*>(image)[i];
@@ -266,29 +266,46 @@ __global__ void __launch_bounds__(256, 2) dune_mma_kernel(const DuneParams prm, 
     }
     __syncthreads();
 
-    // ---- phase 2: M rounds of block-wide arg-min ----------------------------------------------------
+    // ---- phase 2: top-M.  Every warp first reduces the points it computed itself (no block barrier):
+    // M rounds of {lane-local min, REDUX.MIN on the distance bits, REDUX.MIN on the index among the
+    // winners (ties -> lower index)}; then warp 0 merges the nwarps*M candidates the same way.
+    __syncwarp();
     unsigned long long mine = ~0ull;
-    for (int m = 0; m < cnt; ++m) {
-      unsigned long long best = ~0ull;
-      for (int i = tid; i < n; i += nthreads) {
-        const unsigned long long k = keys[i];
-        best = k < best ? k : best;
+    {
+      unsigned long long* cand = cands + warp * M;
+      for (int m = 0; m < cnt; ++m) {
+        unsigned bd = 0xFFFFFFFFu, bi = 0xFFFFFFFFu;
+        for (int ch = warp; ch < chunks; ch += nwarps) {
+          const int i = (ch << 5) + lane;
+          if (i < n) {
+            const uint2 k = *reinterpret_cast<const uint2*>(keys + i);  // .x = index, .y = orderable distance
+            if (k.y < bd) { bd = k.y; bi = k.x; }
+          }
+        }
+        const unsigned md = __reduce_min_sync(0xffffffffu, bd);
+        const unsigned mi = __reduce_min_sync(0xffffffffu, bd == md ? bi : 0xFFFFFFFFu);
+        if (md != 0xFFFFFFFFu && bi == mi && bd == md) keys[mi] = ~0ull;  // the owner retires it
+        if (lane == 0) cand[m] = md == 0xFFFFFFFFu ? ~0ull : (((unsigned long long)md << 32) | mi);
+        __syncwarp();
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-        best = other < best ? other : best;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int total = nwarps * cnt;
+      for (int m = 0; m < cnt; ++m) {
+        unsigned bd = 0xFFFFFFFFu, bi = 0xFFFFFFFFu;
+        int bpos = -1;
+        for (int c = lane; c < total; c += 32) {
+          const int w = c / cnt, r = c - w * cnt;
+          const uint2 k = *reinterpret_cast<const uint2*>(cands + w * M + r);
+          if (k.y < bd || (k.y == bd && k.x < bi)) { bd = k.y; bi = k.x; bpos = w * M + r; }
+        }
+        const unsigned md = __reduce_min_sync(0xffffffffu, bd);
+        const unsigned mi = __reduce_min_sync(0xffffffffu, bd == md ? bi : 0xFFFFFFFFu);
+        if (bpos >= 0 && bd == md && bi == mi) cands[bpos] = ~0ull;
+        if (lane == m) mine = ((unsigned long long)md << 32) | mi;
+        __syncwarp();
       }
-      if (lane == 0) warp_min[m & 1][warp] = best;
-      __syncthreads();
-      best = warp_min[m & 1][0];
-      for (int w = 1; w < nwarps; ++w) {
-        const unsigned long long other = warp_min[m & 1][w];
-        best = other < best ? other : best;
-      }
-      const unsigned idx = (unsigned)(best & 0xffffffffull);
-      if ((int)(idx % nthreads) == tid) keys[idx] = ~0ull;
-      if (tid == m) mine = best;
     }
 
     // ---- phase 3: thread m writes the m-th closest point ---------------------------------------------

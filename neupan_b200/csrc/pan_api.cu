@@ -201,7 +201,7 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
   *out = nullptr;
   if (cfg->receding < 1 || cfg->receding > 32) return fail(NB_ERR_INVALID, "receding must be in 1..32 (got %d)", cfg->receding);
   if (cfg->kinematics < 0 || cfg->kinematics > 2) return fail(NB_ERR_INVALID, "kinematics must be NB_KIN_DIFF/ACKER/OMNI");
-  if (cfg->nrmp_max_num < 0 || cfg->nrmp_max_num > 64) return fail(NB_ERR_INVALID, "nrmp_max_num must be in 0..64");
+  if (cfg->nrmp_max_num < 0 || cfg->nrmp_max_num > 32) return fail(NB_ERR_INVALID, "nrmp_max_num must be in 0..32");
   if (cfg->iter_num < 0) return fail(NB_ERR_INVALID, "iter_num must be >= 0");
   if (cfg->max_envs < 1 || cfg->max_points < 0) return fail(NB_ERR_INVALID, "max_envs >= 1 and max_points >= 0 required");
   if (!(cfg->step_time > 0)) return fail(NB_ERR_INVALID, "step_time must be positive");
