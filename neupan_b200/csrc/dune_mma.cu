@@ -53,23 +53,25 @@ void build_mma_image(const float* w, int E, std::vector<unsigned char>& out) {
 
 int launch_dune_mma(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, cudaStream_t st, char* err,
                     size_t errlen) {
-  const int N = prm.N, E = prm.geo.E;
-  const size_t smem = dune_mma_smem_bytes(N, E, prm.M);
+  const int N = prm.N;
+  const int items = prm.B * (prm.T + 1);
+  int warps = 8;
+  while (warps > 1 && (long long)dune_mma_smem_bytes(N, warps) > max_smem_optin) warps >>= 1;
+  if (items < sm_count * 8) warps = items < sm_count * 2 ? 1 : 2;  // few items: spread the warps over the SMs
+  const size_t smem = dune_mma_smem_bytes(N, warps);
   if ((long long)smem > max_smem_optin) {
     snprintf(err, errlen, "N=%d needs %zu B of shared memory (limit %d)", N, smem, max_smem_optin);
     return -3;
   }
-  int warps = (N + 31) / 32;
-  warps = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
   const int threads = warps * 32;
-  const int items = prm.B * (prm.T + 1);
   cudaError_t e = cudaFuncSetAttribute(dune_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 1;
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dune_mma_kernel, threads, smem);
   if (e == cudaSuccess) {
     if (per_sm < 1) per_sm = 1;
     int grid = sm_count * per_sm;
-    if (grid > items) grid = items;
+    const int need = (items + warps - 1) / warps;
+    if (grid > need) grid = need;
     dune_mma_kernel<<<grid, threads, smem, st>>>(prm, d_image);
     e = cudaGetLastError();
   }

@@ -146,27 +146,70 @@ __device__ __forceinline__ void relu_tile(float (&acc)[4][4]) {
 
 constexpr int kMT = 2;  // 16-row tiles per warp pass: 32 points
 
-__host__ __device__ inline size_t dune_mma_smem_bytes(int N, int E, int M) {
-  return MmaImage::kBytes + (size_t)N * 8 + (((size_t)N * E * 4 + 7) / 8) * 8 + (size_t)kDuneMaxWarps * M * 8 + 16;
+// ObsPointNet for MT 16-row tiles held by one warp: robot-frame coordinates in, mu accumulators out
+// (pre-ReLU; channels t2, t2+1 of rows g / g+8 in mu[mt][0][0..3]).
+template <int MT>
+__device__ __forceinline__ void point_net(const uint4* __restrict__ frag, const float* __restrict__ fl, const float (&x0)[MT][2],
+                                          const float (&y0)[MT][2], float (&mu)[MT][1][4], int lane) {
+  using I = MmaImage;
+  const int t2 = (lane & 3) * 2;
+  float acc[MT][4][4];
+  // layer 0 (2 -> 32) on the FMA pipe, directly in accumulator layout
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 w = *reinterpret_cast<const float4*>(fl + I::W0 + 2 * (8 * j + t2));  // W0[f][0],W0[f][1],W0[f+1][0],W0[f+1][1]
+    const float2 bb = *reinterpret_cast<const float2*>(fl + I::B0 + 8 * j + t2);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      acc[mt][j][0] = fmaf(w.y, y0[mt][0], fmaf(w.x, x0[mt][0], bb.x));
+      acc[mt][j][1] = fmaf(w.w, y0[mt][0], fmaf(w.z, x0[mt][0], bb.y));
+      acc[mt][j][2] = fmaf(w.y, y0[mt][1], fmaf(w.x, x0[mt][1], bb.x));
+      acc[mt][j][3] = fmaf(w.w, y0[mt][1], fmaf(w.z, x0[mt][1], bb.y));
+    }
+  }
+  AFrag a[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) { ln_tanh_tile(acc[mt], fl + I::G1, fl + I::BE1, lane); acc_to_frag(acc[mt], a[mt]); }
+  dense_mma<4, MT>(frag + 0 * I::kHiddenFragU4, fl + I::B3, a, acc, lane);
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) { relu_tile(acc[mt]); acc_to_frag(acc[mt], a[mt]); }
+  dense_mma<4, MT>(frag + 1 * I::kHiddenFragU4, fl + I::B5, a, acc, lane);
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) { ln_tanh_tile(acc[mt], fl + I::G6, fl + I::BE6, lane); acc_to_frag(acc[mt], a[mt]); }
+  dense_mma<4, MT>(frag + 2 * I::kHiddenFragU4, fl + I::B8, a, acc, lane);
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) { relu_tile(acc[mt]); acc_to_frag(acc[mt], a[mt]); }
+  dense_mma<4, MT>(frag + 3 * I::kHiddenFragU4, fl + I::B10, a, acc, lane);
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) { ln_tanh_tile(acc[mt], fl + I::G11, fl + I::BE11, lane); acc_to_frag(acc[mt], a[mt]); }
+  dense_mma<1, MT>(frag + 4 * I::kHiddenFragU4, fl + I::B13, a, mu, lane);
 }
 
+// shared memory: [weight image | per-warp key arrays (N x u64 each)]
+__host__ __device__ inline size_t dune_mma_smem_bytes(int N, int warps) {
+  return MmaImage::kBytes + (size_t)warps * ((size_t)N * 8) + 16;
+}
+
+// One WARP owns one work item (environment b, horizon step t) at a time: it pushes the item's N
+// points through the network 32 at a time, keeps only their (distance, index) keys in its private
+// slice of shared memory, selects the M smallest with REDUX rounds, then re-evaluates the network
+// on those <= 16 points to obtain mu / lambda for the output.  No block-level barrier after the
+// weight image is staged: warps drift apart, so the tensor, MUFU, FMA and ALU phases of different
+// warps overlap on the SM sub-partitions.
 __global__ void __launch_bounds__(256, 2) dune_mma_kernel(const DuneParams prm, const unsigned char* __restrict__ image) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using I = MmaImage;
   const uint4* frag = reinterpret_cast<const uint4*>(smem_raw);
   const float* fl = reinterpret_cast<const float*>(smem_raw + (size_t)I::kFragU4 * 16);
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + I::kBytes);
-  float* smu = reinterpret_cast<float*>(smem_raw + I::kBytes + (size_t)prm.N * 8);
-  unsigned long long* cands = reinterpret_cast<unsigned long long*>(smem_raw + I::kBytes + (size_t)prm.N * 8 + (((size_t)prm.N * prm.geo.E * 4 + 7) / 8) * 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const int g = lane >> 2, t2 = (lane & 3) * 2;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + I::kBytes) + (size_t)warp * prm.N;
+  const int g = lane >> 2, tq = lane & 3, t2 = tq * 2;
   for (int i = tid; i < (int)(I::kBytes / 16); i += nthreads) reinterpret_cast<uint4*>(smem_raw)[i] = reinterpret_cast<const uint4*>(image)[i];
   __syncthreads();
 
   const int T1 = prm.T + 1, N = prm.N, M = prm.M, E = prm.geo.E;
   const int items = prm.B * T1;
-  // this lane's two output channels of the last layer and their geometry rows
-  float Gx[2], Gy[2], hh[2];
+  float Gx[2], Gy[2], hh[2];  // geometry rows of this lane's two output channels
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const int e = t2 + c;
@@ -175,13 +218,13 @@ __global__ void __launch_bounds__(256, 2) dune_mma_kernel(const DuneParams prm, 
     hh[c] = e < E ? prm.geo.h[e] : 0.f;
   }
 
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+  for (int item = blockIdx.x * nwarps + warp; item < items; item += gridDim.x * nwarps) {
     const int b = item / T1, t = item - b * T1;
     if (prm.active && prm.active[b] == 0) continue;
     int n = prm.num_points ? prm.num_points[b] : N;
     n = n < 0 ? 0 : (n > N ? N : n);
     const int cnt = n < M ? n : M;
-    if (t == 0 && tid == 0) {
+    if (t == 0 && lane == 0) {
       prm.sel_count[b] = cnt;
       if (n == 0 && prm.min_dist) prm.min_dist[b] = __int_as_float(0x7f800000);
     }
@@ -194,59 +237,36 @@ __global__ void __launch_bounds__(256, 2) dune_mma_kernel(const DuneParams prm, 
     const float* py = px + N;
     const float* vx = prm.velocities ? prm.velocities + (size_t)b * 2 * N : nullptr;
     const float* vy = vx ? vx + N : nullptr;
+    auto robot_frame = [&](int i, float& gx, float& gy, float& x0, float& y0) {
+      gx = px[i]; gy = py[i];
+      if (vx) {
+        gx = flow(gx, vx[i], prm.dt, t);
+        gy = flow(gy, vy[i], prm.dt, t);
+      }
+      const float dx = gx - sx, dy = gy - sy;  // p0 = R^T (p_t - trans)   (pan.py:210)
+      x0 = fmaf(cs, dx, sn * dy);
+      y0 = fmaf(cs, dy, -(sn * dx));
+    };
 
-    // ---- phase 1: 32 points per warp pass through the network, all in registers ----------------
+    // ---- phase 1: distances of all points, 32 per pass, everything in registers ------------------
     const int chunks = (n + 31) >> 5;
-    for (int ch = warp; ch < chunks; ch += nwarps) {
+#pragma unroll 1
+    for (int ch = 0; ch < chunks; ++ch) {
       const int base = ch << 5;
-      float x0[kMT][2], y0[kMT][2];  // this lane's rows: tile mt, row g (r=0) / g+8 (r=1)
-      float acc[kMT][4][4];
+      float x0[kMT][2], y0[kMT][2];
 #pragma unroll
       for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           int i = base + mt * 16 + r * 8 + g;
           i = i < n ? i : n - 1;
-          float gx = px[i], gy = py[i];
-          if (vx) {
-            gx = flow(gx, vx[i], prm.dt, t);
-            gy = flow(gy, vy[i], prm.dt, t);
-          }
-          const float dx = gx - sx, dy = gy - sy;
-          x0[mt][r] = fmaf(cs, dx, sn * dy);
-          y0[mt][r] = fmaf(cs, dy, -(sn * dx));
+          float gx, gy;
+          robot_frame(i, gx, gy, x0[mt][r], y0[mt][r]);
         }
-      // layer 0 (2 -> 32) on the FMA pipe, directly in accumulator layout
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 w = *reinterpret_cast<const float4*>(fl + I::W0 + 2 * (8 * j + t2));  // W0[f][0],W0[f][1],W0[f+1][0],W0[f+1][1]
-        const float2 bb = *reinterpret_cast<const float2*>(fl + I::B0 + 8 * j + t2);
-#pragma unroll
-        for (int mt = 0; mt < kMT; ++mt) {
-          acc[mt][j][0] = fmaf(w.y, y0[mt][0], fmaf(w.x, x0[mt][0], bb.x));
-          acc[mt][j][1] = fmaf(w.w, y0[mt][0], fmaf(w.z, x0[mt][0], bb.y));
-          acc[mt][j][2] = fmaf(w.y, y0[mt][1], fmaf(w.x, x0[mt][1], bb.x));
-          acc[mt][j][3] = fmaf(w.w, y0[mt][1], fmaf(w.z, x0[mt][1], bb.y));
-        }
-      }
-      AFrag a[kMT];
-#pragma unroll
-      for (int mt = 0; mt < kMT; ++mt) { ln_tanh_tile(acc[mt], fl + I::G1, fl + I::BE1, lane); acc_to_frag(acc[mt], a[mt]); }
-      dense_mma<4, kMT>(frag + 0 * I::kHiddenFragU4, fl + I::B3, a, acc, lane);
-#pragma unroll
-      for (int mt = 0; mt < kMT; ++mt) { relu_tile(acc[mt]); acc_to_frag(acc[mt], a[mt]); }
-      dense_mma<4, kMT>(frag + 1 * I::kHiddenFragU4, fl + I::B5, a, acc, lane);
-#pragma unroll
-      for (int mt = 0; mt < kMT; ++mt) { ln_tanh_tile(acc[mt], fl + I::G6, fl + I::BE6, lane); acc_to_frag(acc[mt], a[mt]); }
-      dense_mma<4, kMT>(frag + 2 * I::kHiddenFragU4, fl + I::B8, a, acc, lane);
-#pragma unroll
-      for (int mt = 0; mt < kMT; ++mt) { relu_tile(acc[mt]); acc_to_frag(acc[mt], a[mt]); }
-      dense_mma<4, kMT>(frag + 3 * I::kHiddenFragU4, fl + I::B10, a, acc, lane);
-#pragma unroll
-      for (int mt = 0; mt < kMT; ++mt) { ln_tanh_tile(acc[mt], fl + I::G11, fl + I::BE11, lane); acc_to_frag(acc[mt], a[mt]); }
       float mu[kMT][1][4];
-      dense_mma<1, kMT>(frag + 4 * I::kHiddenFragU4, fl + I::B13, a, mu, lane);
-      // mu = relu(.), distance = mu^T (G p0 - h): this lane holds channels t2, t2+1 of rows g, g+8
+      point_net<kMT>(frag, fl, x0, y0, mu, lane);
+      // distance = mu^T (G p0 - h): quad-reduce; lane (g, tq) keeps the key of point (mt, r) = (tq>>1, tq&1)
+      float myd = 0.f;
 #pragma unroll
       for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
@@ -256,87 +276,68 @@ __global__ void __launch_bounds__(256, 2) dune_mma_kernel(const DuneParams prm, 
           d = fmaf(m1, fmaf(Gy[1], y0[mt][r], Gx[1] * x0[mt][r]) - hh[1], d);
           d += __shfl_xor_sync(0xffffffffu, d, 1);
           d += __shfl_xor_sync(0xffffffffu, d, 2);
-          const int i = base + mt * 16 + r * 8 + g;
-          if (i < n) {
-            if (t2 < E) smu[i * E + t2] = m0;
-            if (t2 + 1 < E) smu[i * E + t2 + 1] = m1;
-            if ((lane & 3) == 0) keys[i] = ((unsigned long long)orderable(d) << 32) | (unsigned)i;
-          }
+          if (mt * 2 + r == tq) myd = d;
         }
+      const int i = base + (tq >> 1) * 16 + (tq & 1) * 8 + g;
+      if (i < n) keys[i] = ((unsigned long long)orderable(myd) << 32) | (unsigned)i;
     }
-    __syncthreads();
-
-    // ---- phase 2: top-M.  Every warp first reduces the points it computed itself (no block barrier):
-    // M rounds of {lane-local min, REDUX.MIN on the distance bits, REDUX.MIN on the index among the
-    // winners (ties -> lower index)}; then warp 0 merges the nwarps*M candidates the same way.
     __syncwarp();
-    unsigned long long mine = ~0ull;
-    {
-      unsigned long long* cand = cands + warp * M;
-      for (int m = 0; m < cnt; ++m) {
-        unsigned bd = 0xFFFFFFFFu, bi = 0xFFFFFFFFu;
-        for (int ch = warp; ch < chunks; ch += nwarps) {
-          const int i = (ch << 5) + lane;
-          if (i < n) {
-            const uint2 k = *reinterpret_cast<const uint2*>(keys + i);  // .x = index, .y = orderable distance
-            if (k.y < bd) { bd = k.y; bi = k.x; }
-          }
-        }
-        const unsigned md = __reduce_min_sync(0xffffffffu, bd);
-        const unsigned mi = __reduce_min_sync(0xffffffffu, bd == md ? bi : 0xFFFFFFFFu);
-        if (md != 0xFFFFFFFFu && bi == mi && bd == md) keys[mi] = ~0ull;  // the owner retires it
-        if (lane == 0) cand[m] = md == 0xFFFFFFFFu ? ~0ull : (((unsigned long long)md << 32) | mi);
-        __syncwarp();
+
+    // ---- phase 2: the M smallest keys, ascending (ties -> lower index) ------------------------------
+    unsigned sel_idx = 0, sel_ord = 0xFFFFFFFFu;  // lane m holds the m-th closest point
+#pragma unroll 1
+    for (int m = 0; m < cnt; ++m) {
+      unsigned bd = 0xFFFFFFFFu, bi = 0xFFFFFFFFu;
+      for (int i = lane; i < n; i += 32) {
+        const uint2 k = *reinterpret_cast<const uint2*>(keys + i);  // .x = index, .y = orderable distance
+        if (k.y < bd) { bd = k.y; bi = k.x; }
       }
-    }
-    __syncthreads();
-    if (warp == 0) {
-      const int total = nwarps * cnt;
-      for (int m = 0; m < cnt; ++m) {
-        unsigned bd = 0xFFFFFFFFu, bi = 0xFFFFFFFFu;
-        int bpos = -1;
-        for (int c = lane; c < total; c += 32) {
-          const int w = c / cnt, r = c - w * cnt;
-          const uint2 k = *reinterpret_cast<const uint2*>(cands + w * M + r);
-          if (k.y < bd || (k.y == bd && k.x < bi)) { bd = k.y; bi = k.x; bpos = w * M + r; }
-        }
-        const unsigned md = __reduce_min_sync(0xffffffffu, bd);
-        const unsigned mi = __reduce_min_sync(0xffffffffu, bd == md ? bi : 0xFFFFFFFFu);
-        if (bpos >= 0 && bd == md && bi == mi) cands[bpos] = ~0ull;
-        if (lane == m) mine = ((unsigned long long)md << 32) | mi;
-        __syncwarp();
-      }
+      const unsigned md = __reduce_min_sync(0xffffffffu, bd);
+      const unsigned mi = __reduce_min_sync(0xffffffffu, bd == md ? bi : 0xFFFFFFFFu);
+      if (md != 0xFFFFFFFFu && bd == md && bi == mi) keys[mi] = ~0ull;  // the owner lane retires it
+      if (lane == m) { sel_idx = mi; sel_ord = md; }
+      __syncwarp();
     }
 
-    // ---- phase 3: thread m writes the m-th closest point ---------------------------------------------
-    if (tid < cnt) {
-      const unsigned idx = (unsigned)(mine & 0xffffffffull);
-      uint32_t u = (uint32_t)(mine >> 32);
-      u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-      const float d = __uint_as_float(u);
-      float gx = px[idx], gy = py[idx];
-      if (vx) {
-        gx = flow(gx, vx[idx], prm.dt, t);
-        gy = flow(gy, vy[idx], prm.dt, t);
+    // ---- phase 3: mu / lambda of the selected points: one more 16-row tile (row m = m-th closest) ----
+    {
+      float x0[1][2], y0[1][2], gxs[2], gys[2];
+      int rows[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int row = r * 8 + g;
+        unsigned idx = __shfl_sync(0xffffffffu, sel_idx, row < cnt ? row : 0);
+        if (idx >= (unsigned)n) idx = 0;  // all-NaN distances: keep the access in range
+        rows[r] = row;
+        robot_frame((int)idx, gxs[r], gys[r], x0[0][r], y0[0][r]);
       }
-      const size_t o = ((size_t)b * T1 + t) * M + tid;
-      float lx = 0.f, ly = 0.f;
-      for (int e = 0; e < E; ++e) {
-        const float m_e = smu[idx * E + e];
-        const float rgx = fmaf(sn, prm.geo.G[e][1], -cs * prm.geo.G[e][0]);
-        const float rgy = fmaf(-cs, prm.geo.G[e][1], -sn * prm.geo.G[e][0]);
-        lx = fmaf(rgx, m_e, lx);
-        ly = fmaf(rgy, m_e, ly);
-        prm.sel_mu[o * E + e] = m_e;
+      float mu[1][1][4];
+      point_net<1>(frag, fl, x0, y0, mu, lane);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float m0 = fmaxf(mu[0][0][2 * r], 0.f), m1 = fmaxf(mu[0][0][2 * r + 1], 0.f);
+        // lam = ((-R) G^T) mu   (dune.py:89), partial sums over this lane's two channels, then the quad
+        float lx = fmaf(fmaf(sn, Gy[1], -cs * Gx[1]), m1, fmaf(sn, Gy[0], -cs * Gx[0]) * m0);
+        float ly = fmaf(fmaf(-cs, Gy[1], -sn * Gx[1]), m1, fmaf(-cs, Gy[0], -sn * Gx[0]) * m0);
+        lx += __shfl_xor_sync(0xffffffffu, lx, 1); ly += __shfl_xor_sync(0xffffffffu, ly, 1);
+        lx += __shfl_xor_sync(0xffffffffu, lx, 2); ly += __shfl_xor_sync(0xffffffffu, ly, 2);
+        const unsigned ord = __shfl_sync(0xffffffffu, sel_ord, rows[r] < cnt ? rows[r] : 0);
+        if (rows[r] < cnt) {
+          const size_t o = ((size_t)b * T1 + t) * M + rows[r];
+          if (t2 < E) prm.sel_mu[o * E + t2] = m0;
+          if (t2 + 1 < E) prm.sel_mu[o * E + t2 + 1] = m1;
+          if (tq == 0) {
+            const uint32_t u = (ord & 0x80000000u) ? (ord & 0x7fffffffu) : ~ord;
+            const float d = __uint_as_float(u);
+            prm.sel_lam[o * 2 + 0] = lx; prm.sel_lam[o * 2 + 1] = ly;
+            prm.sel_pts[o * 2 + 0] = gxs[r]; prm.sel_pts[o * 2 + 1] = gys[r];
+            prm.sel_dist[o] = d;
+            if (t == 0 && rows[r] == 0 && prm.min_dist) prm.min_dist[b] = d;  // dune.py:97-98
+          }
+        }
       }
-      prm.sel_lam[o * 2 + 0] = lx;
-      prm.sel_lam[o * 2 + 1] = ly;
-      prm.sel_pts[o * 2 + 0] = gx;
-      prm.sel_pts[o * 2 + 1] = gy;
-      prm.sel_dist[o] = d;
-      if (t == 0 && tid == 0 && prm.min_dist) prm.min_dist[b] = d;
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
