@@ -1,0 +1,133 @@
+"""Behavioural parity of the boundary on the GPU: the edge cases the reference's code paths define
+(no points, fewer points than M, ragged batches, decimation, no_obs mode, vector q_s, adjust updates,
+stop criterion + its state across calls, capacity growth)."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_helpers import make_pan, run_pan, to_cuda
+from helpers import CONFIGS, make_inputs, oracle_factory, rel_err
+from oracle import pan as op
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _cmp(got, ref, tol=TOL):
+    S, U, D, md = got
+    So, Uo, Do, mdo, _ = ref
+    B = S.shape[0]
+    return np.array([max(rel_err(S[b], So[b]), rel_err(U[b], Uo[b]), rel_err(D[b], Do[b, 0]),
+                         0.0 if not np.isfinite(mdo[b]) else abs(md[b] - mdo[b])) for b in range(B)])
+
+
+def test_fewer_points_than_M_and_single_point():
+    cfg = CONFIGS["C4"]
+    for N in (1, 4, 9):
+        inp = make_inputs(cfg, B=3, N=N, scene="obstacles")
+        err = _cmp(run_pan(make_pan(cfg, K=1, N=N, max_envs=3), inp), op.run_batch(oracle_factory(cfg, K=1, N=N), inp))
+        assert (err < TOL).all(), (N, err)
+
+
+def test_no_points_and_no_obs_mode():
+    cfg = CONFIGS["C2"]
+    inp = make_inputs(cfg, B=3)
+    inp0 = dict(inp, points=None, velocities=None)
+    pan = make_pan(cfg, K=2, max_envs=3)
+    t = to_cuda(inp)
+    S, U, D = pan(t["nom_s"], t["nom_u"], t["ref_s"], t["ref_us"], None, None)
+    So, Uo, Do, mdo, _ = op.run_batch(oracle_factory(cfg, K=2), inp0)
+    for b in range(3):
+        assert rel_err(S[b].cpu().numpy(), So[b]) < TOL and rel_err(U[b].cpu().numpy(), Uo[b]) < TOL
+        assert rel_err(D[b, 0].cpu().numpy(), Do[b, 0]) < TOL
+    # no_obs mode (nrmp_max_num == 0, pan.py:85): distance output is None, min_distance is inf
+    pan0 = make_pan(cfg, K=2, M=0, max_envs=3)
+    S, U, D = pan0(t["nom_s"], t["nom_u"], t["ref_s"], t["ref_us"], t["points"], t["velocities"])
+    assert D is None and pan0.min_distance == float("inf") and pan0.dune_points is None and pan0.nrmp_points is None
+    So, Uo, _, _, _ = op.run_batch(oracle_factory(cfg, K=2, M=0), inp)
+    for b in range(3):
+        assert rel_err(S[b].cpu().numpy(), So[b]) < TOL and rel_err(U[b].cpu().numpy(), Uo[b]) < TOL
+
+
+def test_ragged_batch_equals_truncated_single_envs():
+    cfg = CONFIGS["C4"]
+    B, N = 5, 64
+    inp = make_inputs(cfg, B=B, N=N, scene="obstacles")
+    counts = np.array([64, 10, 0, 33, 3], np.int32)
+    pan = make_pan(cfg, K=1, N=N, max_envs=B)
+    t = to_cuda(inp)
+    S, U, D = pan(t["nom_s"], t["nom_u"], t["ref_s"], t["ref_us"], t["points"], t["velocities"], num_points=torch.from_numpy(counts).cuda())
+    md = pan.min_distance.cpu().numpy()
+    for b in range(B):
+        one = {k: (None if v is None else v[b:b + 1]) for k, v in inp.items()}
+        n = int(counts[b])
+        one["points"] = one["points"][:, :, :n] if n else None
+        one["velocities"] = one["velocities"][:, :, :n] if n else None
+        So, Uo, Do, mdo, _ = op.run_batch(oracle_factory(cfg, K=1, N=max(n, 1)), one)
+        assert rel_err(S[b].cpu().numpy(), So[0]) < TOL and rel_err(U[b].cpu().numpy(), Uo[0]) < TOL, b
+        assert rel_err(D[b, 0].cpu().numpy(), Do[0, 0]) < TOL
+        assert (np.isinf(md[b]) and n == 0) or abs(md[b] - mdo[0]) < TOL
+    assert pan.read_selection()["count"].cpu().tolist() == [10, 10, 0, 10, 3]
+
+
+def test_decimation_to_dune_max_num():
+    cfg = CONFIGS["C1"]
+    inp = make_inputs(cfg, B=2, N=300)
+    pan = make_pan(cfg, K=1, max_envs=2, dune_max_num=100, N=300)
+    got = run_pan(pan, inp)
+    ref = op.run_batch(oracle_factory(cfg, K=1, N=100), inp)  # the oracle decimates like pan.py:171-174
+    assert (_cmp(got, ref) < TOL).all()
+    assert pan.dune_points[0].shape == (2, 100)
+
+
+def test_vector_qs_and_adjust_update():
+    cfg = CONFIGS["C4"]
+    inp = make_inputs(cfg, B=3, scene="obstacles")
+    adj = dict(cfg.adjust, q_s=[0.5, 0.6, 0.1])
+    pan = make_pan(cfg, K=1, max_envs=3, adjust=adj)
+    assert (_cmp(run_pan(pan, inp), op.run_batch(oracle_factory(cfg, K=1, adjust=adj), inp)) < TOL).all()
+    new = dict(q_s=[1.0, 0.2, 0.3], p_u=0.7, eta=8.0, d_max=0.8, d_min=0.05)
+    pan.nrmp_layer.update_adjust_parameters_value(**new)
+    pan.reset_state()
+    assert (_cmp(run_pan(pan, inp), op.run_batch(oracle_factory(cfg, K=1, adjust=dict(cfg.adjust, **new)), inp)) < TOL).all()
+    assert len(pan.nrmp_layer.adjust_parameters) == 5 and pan.nrmp_layer.adjust_parameters[1].item() == pytest.approx(0.7)
+    with pytest.raises(ValueError):
+        pan.nrmp_layer.update_adjust_parameters_value(q_s=[1.0, 2.0])
+
+
+def test_stop_criterion_and_state_across_calls():
+    """iter_threshold = 0.1 (yaml default): per-env early stop, and PAN.current_nom_values persisting
+    from one forward() to the next (pan.py:100-105, 215-243)."""
+    cfg = CONFIGS["C5"]  # omni: the iteration contracts, so the criterion actually fires
+    B = 12
+    inp = make_inputs(cfg, B=B, scene="obstacles")
+    pan = make_pan(cfg, K=6, iter_threshold=0.1, max_envs=B)
+    mk = oracle_factory(cfg, K=6, iter_threshold=0.1)
+    oracles = [mk() for _ in range(B)]
+    for call in range(2):
+        S, U, D, md = run_pan(pan, inp)
+        it = pan.iterations.cpu().numpy()
+        same = 0
+        for b in range(B):
+            o = oracles[b]
+            vel = None if inp["velocities"] is None else inp["velocities"][b]
+            So, Uo, Do = o.forward(inp["nom_s"][b], inp["nom_u"][b], inp["ref_s"][b], inp["ref_us"][b], inp["points"][b], vel)
+            if it[b] == o.iters_run:
+                same += 1
+        assert same >= 0.8 * B, (call, it)
+        assert it.min() >= 1 and it.max() <= 6
+    assert it.min() < 6  # second call: the stored state lets some envs stop early
+    pan.reset_state()
+    run_pan(pan, inp)
+    assert pan.iterations.cpu().numpy().min() >= 2  # first call after a reset never stops at iteration 1
+
+
+def test_capacity_growth_and_shape_checks():
+    cfg = CONFIGS["C1"]
+    pan = make_pan(cfg, K=1, max_envs=1)
+    a = run_pan(pan, make_inputs(cfg, B=1))
+    b = run_pan(pan, make_inputs(cfg, B=4))  # exceeds max_envs: the native handle is re-created
+    assert np.array_equal(a[0][0], b[0][0])
+    with pytest.raises(AssertionError):
+        pan(torch.zeros(3, 7).cuda(), torch.zeros(2, 10).cuda(), torch.zeros(3, 11).cuda(), torch.zeros(10).cuda())
+    assert (pan.status.cpu().numpy() == 0).all()
