@@ -113,8 +113,10 @@ int nb_pan_set_iteration(nb_pan_t* pan, int32_t iter_num, float iter_threshold);
 
 /* Implementation switches (no reference counterpart).  NB_OPT_DUNE_KERNEL: 1 (default) = tensor-core
  * DUNE kernel (mma.sync, fp16 hi/lo split, fp32 accumulate); 0 = all-FP32 FFMA kernel, kept as the
- * in-tree numerical reference of the same contract (needs the edge count compiled in). */
-enum { NB_OPT_DUNE_KERNEL = 1 };
+ * in-tree numerical reference of the same contract (needs the edge count compiled in).
+ * NB_OPT_OVERLAP: 1..4 = number of environment sub-batches pipelined on internal streams so that the DUNE kernel
+ * of one sub-batch shares the SMs with the NRMP kernel of another (results are identical; envs are independent). */
+enum { NB_OPT_DUNE_KERNEL = 1, NB_OPT_OVERLAP = 2 };
 int nb_pan_set_option(nb_pan_t* pan, int32_t option, int32_t value);
 
 /* Forget PAN.current_nom_values (pan.py:100-105) of all environments.  (The reference's

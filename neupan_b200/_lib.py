@@ -17,6 +17,7 @@ NB_KIN = {"diff": 0, "acker": 1, "omni": 2}
 NB_OK, NB_ERR_INVALID, NB_ERR_CUDA, NB_ERR_CAPACITY, NB_ERR_NO_DEVICE = 0, -1, -2, -3, -4
 STATUS_MAXITER, STATUS_NUMERIC, STATUS_INFEASIBLE = 1, 2, 4
 OPT_DUNE_KERNEL = 1
+OPT_OVERLAP = 2
 
 
 class PanConfig(C.Structure):

@@ -63,6 +63,7 @@ class PAN(torch.nn.Module):
             dev = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
         self.device = torch.device("cuda", dev.index if dev.index is not None else 0)
         self._handle = None
+        self.overlap = int(kwargs.get("overlap", 1))  # env sub-batches pipelined on internal streams (1 = off)
         self.dune_kernel = int(kwargs.get("dune_kernel", 1))  # 1 = tensor-core DUNE kernel, 0 = all-FP32 FFMA kernel
         self._cap = (max(1, int(kwargs.get("max_envs", 1))), max(1, int(kwargs.get("max_points", max(1, dune_max_num)))))
         self._sent = None  # (adjust version, iter_num, iter_threshold) last pushed to the handle
@@ -111,6 +112,7 @@ class PAN(torch.nn.Module):
         self._handle, self._cap = handle, (cap_b, cap_n)
         if not self.no_obs:
             _lib.check(lib.nb_pan_set_option(handle, _lib.OPT_DUNE_KERNEL, int(self.dune_kernel)))
+        _lib.check(lib.nb_pan_set_option(handle, _lib.OPT_OVERLAP, int(self.overlap)))
         self._sent = (self.nrmp_layer.version, int(self.iter_num), float(self.iter_threshold))
         return lib
 

@@ -1,5 +1,6 @@
 // Translation unit of the tensor-core DUNE kernel: host-side weight image + launcher.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -51,8 +52,8 @@ void build_mma_image(const float* w, int E, std::vector<unsigned char>& out) {
   cp(I::B13, L::b13(E), E);
 }
 
-int launch_dune_mma(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, cudaStream_t st, char* err,
-                    size_t errlen) {
+int launch_dune_mma(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, int cta_per_sm_limit,
+                    cudaStream_t st, char* err, size_t errlen) {
   const int N = prm.N;
   const int items = prm.B * (prm.T + 1);
   int warps = 8;
@@ -64,15 +65,22 @@ int launch_dune_mma(const DuneParams& prm, const unsigned char* d_image, int sm_
     return -3;
   }
   const int threads = warps * 32;
-  cudaError_t e = cudaFuncSetAttribute(dune_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static int variant = -1;  // NB_DUNE_MT: developer switch between the 32-point (2 tiles) and 16-point (1 tile) warp pass
+  if (variant < 0) {
+    const char* v = getenv("NB_DUNE_MT");
+    variant = v ? atoi(v) : 2;
+  }
+  auto kern = variant == 1 ? dune_mma_kernel<1, 3> : dune_mma_kernel<2, 2>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 1;
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dune_mma_kernel, threads, smem);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
   if (e == cudaSuccess) {
     if (per_sm < 1) per_sm = 1;
+    if (cta_per_sm_limit > 0 && per_sm > cta_per_sm_limit) per_sm = cta_per_sm_limit;
     int grid = sm_count * per_sm;
     const int need = (items + warps - 1) / warps;
     if (grid > need) grid = need;
-    dune_mma_kernel<<<grid, threads, smem, st>>>(prm, d_image);
+    kern<<<grid, threads, smem, st>>>(prm, d_image);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {

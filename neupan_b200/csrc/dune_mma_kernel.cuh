@@ -40,7 +40,7 @@ struct MmaImage {
 };
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -144,7 +144,6 @@ __device__ __forceinline__ void relu_tile(float (&acc)[4][4]) {
     for (int c = 0; c < 4; ++c) acc[j][c] = fmaxf(acc[j][c], 0.f);
 }
 
-constexpr int kMT = 2;  // 16-row tiles per warp pass: 32 points
 
 // ObsPointNet for MT 16-row tiles held by one warp: robot-frame coordinates in, mu accumulators out
 // (pre-ReLU; channels t2, t2+1 of rows g / g+8 in mu[mt][0][0..3]).
@@ -196,7 +195,8 @@ __host__ __device__ inline size_t dune_mma_smem_bytes(int N, int warps) {
 // on those <= 16 points to obtain mu / lambda for the output.  No block-level barrier after the
 // weight image is staged: warps drift apart, so the tensor, MUFU, FMA and ALU phases of different
 // warps overlap on the SM sub-partitions.
-__global__ void __launch_bounds__(256, 2) dune_mma_kernel(const DuneParams prm, const unsigned char* __restrict__ image) {
+template <int kMT, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) dune_mma_kernel(const DuneParams prm, const unsigned char* __restrict__ image) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using I = MmaImage;
   const uint4* frag = reinterpret_cast<const uint4*>(smem_raw);
@@ -249,10 +249,11 @@ __global__ void __launch_bounds__(256, 2) dune_mma_kernel(const DuneParams prm, 
     };
 
     // ---- phase 1: distances of all points, 32 per pass, everything in registers ------------------
-    const int chunks = (n + 31) >> 5;
+    constexpr int kPts = 16 * kMT;  // points per pass
+    const int chunks = (n + kPts - 1) / kPts;
 #pragma unroll 1
     for (int ch = 0; ch < chunks; ++ch) {
-      const int base = ch << 5;
+      const int base = ch * kPts;
       float x0[kMT][2], y0[kMT][2];
 #pragma unroll
       for (int mt = 0; mt < kMT; ++mt)
@@ -278,8 +279,9 @@ __global__ void __launch_bounds__(256, 2) dune_mma_kernel(const DuneParams prm, 
           d += __shfl_xor_sync(0xffffffffu, d, 2);
           if (mt * 2 + r == tq) myd = d;
         }
+      // lane (g, tq) stores the key of point (mt, r) = (tq>>1, tq&1); with one tile only tq < 2 own a point
       const int i = base + (tq >> 1) * 16 + (tq & 1) * 8 + g;
-      if (i < n) keys[i] = ((unsigned long long)orderable(myd) << 32) | (unsigned)i;
+      if (i < n && (tq >> 1) < kMT) keys[i] = ((unsigned long long)orderable(myd) << 32) | (unsigned)i;
     }
     __syncwarp();
 

@@ -17,7 +17,8 @@
 namespace nb {
 // dune_mma.cu
 void build_mma_image(const float* w, int E, std::vector<unsigned char>& out);
-int launch_dune_mma(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, cudaStream_t st, char* err, size_t errlen);
+int launch_dune_mma(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, int cta_per_sm_limit, cudaStream_t st,
+                    char* err, size_t errlen);
 }  // namespace nb
 
 namespace {
@@ -55,6 +56,9 @@ struct nb_pan {
   float* d_weights = nullptr;
   unsigned char* d_image = nullptr;  // fragment-ordered fp16 hi/lo weight image of the tensor-core DUNE kernel
   int dune_variant = 1;              // NB_OPT_DUNE_KERNEL: 0 = FP32 FFMA kernel, 1 = tensor-core kernel
+  int overlap = 1;                   // NB_OPT_OVERLAP: number of env sub-batches pipelined on internal streams
+  cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   float *sel_mu = nullptr, *sel_lam = nullptr, *sel_pts = nullptr, *sel_dist = nullptr;
   int32_t* sel_count = nullptr;
   float *prev_s = nullptr, *prev_u = nullptr, *prev_mu = nullptr, *prev_lam = nullptr;
@@ -84,11 +88,11 @@ int check_forward_args(const nb_pan* p, int B, int N) {
 #define NB_EDGE_MASK 0x10
 #endif
 
-int launch_dune(nb_pan* p, const nb::DuneParams& prm, cudaStream_t st) {
+int launch_dune(nb_pan* p, const nb::DuneParams& prm, cudaStream_t st, int cta_limit = 0) {
   int rc = NB_ERR_INVALID;
   char msg[256] = "";
   if (p->dune_variant == 1) {
-    rc = nb::launch_dune_mma(prm, p->d_image, p->sm_count, p->max_smem_optin, st, msg, sizeof(msg));
+    rc = nb::launch_dune_mma(prm, p->d_image, p->sm_count, p->max_smem_optin, cta_limit, st, msg, sizeof(msg));
     if (rc) return fail(rc, "%s", msg);
     ++g_launches;
     return NB_OK;
@@ -264,6 +268,11 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
 int nb_pan_destroy(nb_pan_t* p) {
   if (!p) return NB_OK;
   cudaSetDevice(p->cfg.device);
+  for (int i = 0; i < 4; ++i) {
+    if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
+    if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
+  }
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   void* bufs[] = {p->d_image, p->d_weights, p->sel_mu, p->sel_lam, p->sel_pts, p->sel_dist, p->sel_count, p->prev_s, p->prev_u, p->prev_mu,
                   p->prev_lam, p->prev_count, p->prev_valid, p->active, p->iters, p->status, p->ipm_it, p->min_dist, p->h_in, p->h_out, p->h_np, p->h_io};
   for (void* b : bufs)
@@ -290,6 +299,17 @@ int nb_pan_set_option(nb_pan_t* p, int32_t option, int32_t value) {
   if (option == NB_OPT_DUNE_KERNEL) {
     if (value != 0 && value != 1) return fail(NB_ERR_INVALID, "NB_OPT_DUNE_KERNEL takes 0 (fp32 ffma) or 1 (tensor core)");
     p->dune_variant = value;
+    return NB_OK;
+  }
+  if (option == NB_OPT_OVERLAP) {
+    if (value < 1 || value > 4) return fail(NB_ERR_INVALID, "NB_OPT_OVERLAP takes 1..4");
+    NB_CUDA(cudaSetDevice(p->cfg.device));
+    for (int i = 0; i < value && value > 1; ++i) {
+      if (!p->streams[i]) NB_CUDA(cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking));
+      if (!p->ev_join[i]) NB_CUDA(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
+    }
+    if (value > 1 && !p->ev_fork) NB_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    p->overlap = value;
     return NB_OK;
   }
   return fail(NB_ERR_INVALID, "unknown option %d", option);
@@ -350,25 +370,53 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
   NB_CUDA(cudaMemcpyAsync(out_s, nom_s, (size_t)B * 3 * T1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   NB_CUDA(cudaMemcpyAsync(out_u, nom_u, (size_t)B * 2 * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
   NB_CUDA(cudaMemsetAsync(out_d, 0, (size_t)B * T * sizeof(float), st));
-  for (int k = 0; k < c.iter_num; ++k) {
-    if (with_dune) {
-      nb::DuneParams d{};
-      d.weights = p->d_weights; d.nom_s = out_s; d.points = points; d.velocities = velocities; d.num_points = num_points;
-      d.active = p->active;
-      d.sel_mu = p->sel_mu; d.sel_lam = p->sel_lam; d.sel_pts = p->sel_pts; d.sel_dist = p->sel_dist; d.sel_count = p->sel_count;
-      d.min_dist = p->min_dist;
-      d.B = B; d.N = N; d.T = T; d.M = c.nrmp_max_num; d.dt = (float)c.step_time; d.geo = p->geo;
-      if (int rc = launch_dune(p, d, st)) return rc;
+  // K iterations of {DUNE, NRMP} for the environments [lo, hi) on stream s
+  auto run_range = [&](int lo, int hi, cudaStream_t s, int dune_cta_limit) -> int {
+    const int nb_ = hi - lo;
+    const size_t T1s = (size_t)T1, Ms = (size_t)c.nrmp_max_num, Es = (size_t)(c.edge_dim > 0 ? c.edge_dim : 1);
+    for (int k = 0; k < c.iter_num; ++k) {
+      if (with_dune) {
+        nb::DuneParams d{};
+        d.weights = p->d_weights; d.nom_s = out_s + (size_t)lo * 3 * T1s; d.points = points + (size_t)lo * 2 * N;
+        d.velocities = velocities ? velocities + (size_t)lo * 2 * N : nullptr;
+        d.num_points = num_points ? num_points + lo : nullptr;
+        d.active = p->active + lo;
+        d.sel_mu = p->sel_mu + (size_t)lo * T1s * Ms * Es; d.sel_lam = p->sel_lam + (size_t)lo * T1s * Ms * 2;
+        d.sel_pts = p->sel_pts + (size_t)lo * T1s * Ms * 2; d.sel_dist = p->sel_dist + (size_t)lo * T1s * Ms; d.sel_count = p->sel_count + lo;
+        d.min_dist = p->min_dist + lo;
+        d.B = nb_; d.N = N; d.T = T; d.M = c.nrmp_max_num; d.dt = (float)c.step_time; d.geo = p->geo;
+        if (int rc = launch_dune(p, d, s, dune_cta_limit)) return rc;
+      }
+      nb::NrmpParams n{};
+      n.nom_s = out_s + (size_t)lo * 3 * T1s; n.nom_u = out_u + (size_t)lo * 2 * T; n.ref_s = ref_s + (size_t)lo * 3 * T1s; n.ref_us = ref_us + (size_t)lo * T;
+      if (with_dune) {
+        n.sel_mu = p->sel_mu + (size_t)lo * T1s * Ms * Es; n.sel_lam = p->sel_lam + (size_t)lo * T1s * Ms * 2;
+        n.sel_pts = p->sel_pts + (size_t)lo * T1s * Ms * 2; n.sel_count = p->sel_count + lo;
+      }
+      n.out_s = out_s + (size_t)lo * 3 * T1s; n.out_u = out_u + (size_t)lo * 2 * T; n.out_d = out_d + (size_t)lo * T;
+      n.status = p->status + lo; n.iters = p->iters + lo; n.active = p->active + lo; n.ipm_iters = p->ipm_it + lo;
+      n.prev_s = p->prev_s + (size_t)lo * 3 * T1s; n.prev_u = p->prev_u + (size_t)lo * 2 * T;
+      n.prev_mu = p->prev_mu + (size_t)lo * T1s * Ms * Es; n.prev_lam = p->prev_lam + (size_t)lo * T1s * Ms * 2;
+      n.prev_count = p->prev_count + lo; n.prev_valid = p->prev_valid + lo;
+      n.B = nb_;
+      if (int rc = launch_nrmp(p, n, s)) return rc;
     }
-    nb::NrmpParams n{};
-    n.nom_s = out_s; n.nom_u = out_u; n.ref_s = ref_s; n.ref_us = ref_us;
-    if (with_dune) { n.sel_mu = p->sel_mu; n.sel_lam = p->sel_lam; n.sel_pts = p->sel_pts; n.sel_count = p->sel_count; }
-    n.out_s = out_s; n.out_u = out_u; n.out_d = out_d; n.status = p->status; n.iters = p->iters; n.active = p->active;
-    n.ipm_iters = p->ipm_it;
-    n.prev_s = p->prev_s; n.prev_u = p->prev_u; n.prev_mu = p->prev_mu; n.prev_lam = p->prev_lam;
-    n.prev_count = p->prev_count; n.prev_valid = p->prev_valid;
-    n.B = B;
-    if (int rc = launch_nrmp(p, n, st)) return rc;
+    return NB_OK;
+  };
+  const int parts = (p->overlap > 1 && with_dune && B >= 64 * p->overlap) ? p->overlap : 1;
+  if (parts == 1) {
+    if (int rc = run_range(0, B, st, 0)) return rc;
+  } else {
+    // sub-batches on internal streams: the DUNE kernel of one part (issue / tensor / MUFU bound) shares the SMs with the
+    // NRMP kernel of another (latency bound, few warps)
+    NB_CUDA(cudaEventRecord(p->ev_fork, st));
+    for (int i = 0; i < parts; ++i) {
+      NB_CUDA(cudaStreamWaitEvent(p->streams[i], p->ev_fork, 0));
+      const int lo = (int)((long long)B * i / parts), hi = (int)((long long)B * (i + 1) / parts);
+      if (int rc = run_range(lo, hi, p->streams[i], 1)) return rc;
+      NB_CUDA(cudaEventRecord(p->ev_join[i], p->streams[i]));
+      NB_CUDA(cudaStreamWaitEvent(st, p->ev_join[i], 0));
+    }
   }
   finish_run_kernel<<<gb, tb, 0, st>>>(B, p->iters, p->status, p->min_dist, out_iters, out_status, out_min_distance);
   ++g_launches;
