@@ -131,3 +131,32 @@ def test_capacity_growth_and_shape_checks():
     with pytest.raises(AssertionError):
         pan(torch.zeros(3, 7).cuda(), torch.zeros(2, 10).cuda(), torch.zeros(3, 11).cuda(), torch.zeros(10).cuda())
     assert (pan.status.cpu().numpy() == 0).all()
+
+
+@pytest.mark.parametrize("dune_kernel", [1, 0])
+def test_pentagon_robot_five_edges_random_weights(dune_kernel, tmp_path):
+    """E = 5 (no shipped checkpoint has E != 4): a randomly initialised ObsPointNet(2, 5) saved in the
+    reference's checkpoint format, run through both DUNE kernels and the oracle."""
+    import types
+
+    from neupan_b200 import PAN, ObsPointNet, robot
+    from oracle import dune as od, nrmp as onr
+
+    torch.manual_seed(11)
+    net = ObsPointNet(2, 5)
+    ck = str(tmp_path / "model_pentagon.pth")
+    torch.save(net.state_dict(), ck)
+    verts = [[1.2, 0.0], [0.4, 1.1], [-0.9, 0.7], [-0.9, -0.7], [0.4, -1.1]]
+    rb = robot(10, 0.1, kinematics="diff", vertices=verts, max_speed=[8, 3], max_acce=[8, 3])
+    assert rb.G.shape == (5, 2)
+    cfg = CONFIGS["C4"]
+    B, N = 4, 96
+    inp = make_inputs(cfg, B=B, N=N, scene="obstacles")
+    pan = PAN(10, 0.1, rb, iter_num=1, dune_max_num=N, nrmp_max_num=10, dune_checkpoint=ck, iter_threshold=0.0,
+              adjust_kwargs=dict(cfg.adjust), max_envs=B, max_points=N, dune_kernel=dune_kernel)
+    got = run_pan(pan, inp)
+    spec = onr.RobotSpec("diff", rb.G, rb.h, rb.max_speed.reshape(-1), rb.max_acce.reshape(-1), 0.1, None)
+    w = od.load_weights(ck)
+    mk = lambda: op.OraclePAN(spec, w, T=10, iter_num=1, dune_max_num=N, nrmp_max_num=10, iter_threshold=0.0, adjust=onr.Adjust(**cfg.adjust))
+    assert (_cmp(got, op.run_batch(mk, inp)) < TOL).all()
+    assert pan.read_selection()["mu"].shape == (B, 11, 10, 5)
