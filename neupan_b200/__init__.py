@@ -7,7 +7,8 @@ need a GPU; running PAN does -- there is no CPU fallback.
 """
 from . import configuration, util
 from .robot import robot
-from .blocks import DUNE, NRMP, PAN, ObsPointNet
+from .blocks import DUNE, NRMP, PAN, InitialPath, ObsPointNet
+from .neupan import neupan
 
-__all__ = ["configuration", "util", "robot", "PAN", "DUNE", "NRMP", "ObsPointNet"]
+__all__ = ["configuration", "util", "robot", "neupan", "PAN", "DUNE", "NRMP", "ObsPointNet", "InitialPath"]
 __version__ = "0.1.0"

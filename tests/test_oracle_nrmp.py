@@ -96,7 +96,7 @@ def test_oracle_pan_trace_regression(cname, scene):
 
 def test_oracle_iteration_amplifies_perturbations():
     """Documents why end-to-end K-iteration parity can only be statistical: ONE oracle PAN iteration
-    maps a 1e-6 relative perturbation of its nominal input to a >10x larger change of its output in
+    maps a 1e-6 relative perturbation of its nominal input (s, u) to a > 10x larger change of its output in
     cluttered / acker scenes (re-linearisation + penalty rho = 400), independent of any GPU code."""
     cfg = CONFIGS["C2"]
     inp = make_inputs(cfg, B=8, scene="obstacles")
@@ -108,6 +108,7 @@ def test_oracle_iteration_amplifies_perturbations():
         base = oracle_factory(cfg, K=1)().forward(s1, u1, inp["ref_s"][b], inp["ref_us"][b], inp["points"][b], vel)
         rng = np.random.default_rng(b)
         du = (1e-6 * np.abs(u1).max() * rng.standard_normal(u1.shape)).astype(np.float32)
-        pert = oracle_factory(cfg, K=1)().forward(s1, u1 + du, inp["ref_s"][b], inp["ref_us"][b], inp["points"][b], vel)
-        amp.append(np.abs(pert[1] - base[1]).max() / np.abs(du).max())
-    assert max(amp) > 5.0, amp
+        ds = (1e-6 * np.abs(s1).max() * rng.standard_normal(s1.shape)).astype(np.float32)
+        pert = oracle_factory(cfg, K=1)().forward(s1 + ds, u1 + du, inp["ref_s"][b], inp["ref_us"][b], inp["points"][b], vel)
+        amp.append(np.abs(pert[1] - base[1]).max() / max(np.abs(du).max(), np.abs(ds).max()))
+    assert max(amp) > 10.0, amp  # measured: 1x .. 46x over these 8 environments
