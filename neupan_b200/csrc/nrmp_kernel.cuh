@@ -124,11 +124,15 @@ __device__ __forceinline__ float rcpf(double x) {
 
 // SMALL: 2T <= 32, every lane owns at most one row of the reduced system (one register slot in the
 // triangular solves); the general version (T <= 32) carries a second slot.
-template <int HPL, bool SMALL>
-__global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpParams prm, int warps_per_cta, int warp_doubles) {
+// TT, MM: compile-time horizon / hinge rows per step (0 = read them from the parameters).  With constants every
+// workspace offset, loop bound and row stride folds into immediates -- half of the generic kernel's
+// instructions were integer address arithmetic.
+template <int HPL, bool SMALL, int TT, int MM>
+__global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpParams prm, int warps_per_cta, int warp_doubles_rt) {
   extern __shared__ __align__(16) double smem_d[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int T = prm.T, M = prm.M, T1 = T + 1;
+  const int T = TT > 0 ? TT : prm.T, M = TT > 0 ? MM : prm.M, T1 = T + 1;
+  const int warp_doubles = TT > 0 ? (int)nrmp_warp_doubles(TT, MM) : warp_doubles_rt;
   const int nU = 2 * T, nR = nU - 2, TD = M > 0 ? T : 0, TM = T * M;
   const int nP = nU * (nU + 1) / 2;
   const int oBU = 0, oBL = nU, oRU = 2 * nU, oRL = oRU + nR, oDU = oRL + nR, oDL = oDU + TD;

@@ -161,15 +161,18 @@ int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st) {
     return NB_OK;
   };
   const int hpl = (TM + 31) / 32;
+  // specialisations with compile-time (T, M) for the reference's shipped configurations
+  if (prm.T == 10 && prm.M == 10) return go(nb::nrmp_kernel<4, true, 10, 10>);
+  if (prm.T == 15 && prm.M == 10) return go(nb::nrmp_kernel<5, true, 15, 10>);
   if (prm.T <= 16) {  // 2T <= 32: one row of the reduced system per lane
-    if (hpl <= 1) return go(nb::nrmp_kernel<1, true>);
-    if (hpl <= 2) return go(nb::nrmp_kernel<2, true>);
-    if (hpl <= 4) return go(nb::nrmp_kernel<4, true>);
-    if (hpl <= 5) return go(nb::nrmp_kernel<5, true>);
-    return go(nb::nrmp_kernel<8, true>);
+    if (hpl <= 1) return go(nb::nrmp_kernel<1, true, 0, 0>);
+    if (hpl <= 2) return go(nb::nrmp_kernel<2, true, 0, 0>);
+    if (hpl <= 4) return go(nb::nrmp_kernel<4, true, 0, 0>);
+    if (hpl <= 5) return go(nb::nrmp_kernel<5, true, 0, 0>);
+    return go(nb::nrmp_kernel<8, true, 0, 0>);
   }
-  if (hpl <= 4) return go(nb::nrmp_kernel<4, false>);
-  return go(nb::nrmp_kernel<8, false>);
+  if (hpl <= 4) return go(nb::nrmp_kernel<4, false, 0, 0>);
+  return go(nb::nrmp_kernel<8, false, 0, 0>);
 }
 
 __global__ void init_run_kernel(int B, int32_t* active, int32_t* iters, int32_t* status, float* min_dist, int32_t* sel_count) {
