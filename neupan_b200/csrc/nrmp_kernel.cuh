@@ -57,7 +57,7 @@ struct NrmpParams {
 
 // per-warp shared memory, in doubles
 __host__ __device__ inline size_t nrmp_scratch_doubles(int T, int M) {
-  size_t sc = 2 * (size_t)T * (2 * T);  // Gx,Gy; also holds per-hinge scratch (T*M) and the setup-only linearisation (12 T)
+  size_t sc = 2 * (size_t)T * (T + 1);  // Gx,Gy (packed like F); also holds per-hinge scratch (T*M) and the setup-only linearisation (12 T)
   if (sc < (size_t)T * M) sc = (size_t)T * M;
   if (sc < 12 * (size_t)T) sc = 12 * (size_t)T;
   return sc;
@@ -66,7 +66,7 @@ __host__ __device__ inline size_t nrmp_warp_doubles(int T, int M) {
   const int nU = 2 * T, nR = nU - 2, TD = M > 0 ? T : 0, TM = T * M;
   const int mb = 2 * nU + 2 * nR + 2 * TD;
   size_t n = 0;
-  n += 3 * (size_t)T * nU;         // F
+  n += 3 * (size_t)T * (T + 1);    // F, packed: row t keeps only its 2(t+1) structurally non-zero columns at offset t(t+1)
   n += 3 * (size_t)T;              // s0
   n += (size_t)nU * (nU + 1) / 2;  // Hc
   n += (size_t)nU * (nU + 1);      // H (padded rows)
@@ -76,8 +76,8 @@ __host__ __device__ inline size_t nrmp_warp_doubles(int T, int M) {
   n += 4 * (size_t)mb;             // s, z, ds, dz of the box / rate / D rows
   n += ((size_t)mb + 1) / 2;       // is (float)
   n += (size_t)TM;                 // fax, fay (float)
-  n += ((size_t)mb + 1) / 2;       // row-enable flags (float)
-  return n + 4;
+  n += ((size_t)mb + 7) / 8;       // row-enable flags (bytes)
+  return n + 1;
 }
 __host__ __device__ inline size_t nrmp_cta_extra_bytes(int T) {  // pair table (uint16) shared by the CTA's warps
   const int nU = 2 * T;
@@ -155,12 +155,13 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
 
   // ---- carve this warp's workspace -------------------------------------------------------
   double* wsp = smem_d + (size_t)warp * warp_doubles;
-  double* F = wsp;            wsp += 3 * T * nU;   // F[r][t][j]
+  const int FT = T * (T + 1);                      // packed size of one component of F / G
+  double* F = wsp;            wsp += 3 * FT;       // F[r][t][j] at r*FT + t(t+1) + j, j < 2(t+1)  (zero beyond)
   double* s0 = wsp;           wsp += 3 * T;        // s0[r][t]
   double* Hc = wsp;           wsp += nP;
   double* H = wsp;            wsp += nU * HS;
   double* scratch = wsp;      wsp += nrmp_scratch_doubles(T, M);
-  double* Gx = scratch;  double* Gy = scratch + T * nU;  // Hessian assembly
+  double* Gx = scratch;  double* Gy = scratch + FT;  // Hessian assembly (same packing as F)
   double* tmpk = scratch;                                // per-hinge values published for the per-step sums
   double* cv = wsp;           wsp += nU;
   double* x = wsp;            wsp += nU;
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
   float* cis = reinterpret_cast<float*>(wsp);  wsp += (mb + 1) / 2;  // inverse slacks
   float* fax_s = reinterpret_cast<float*>(wsp);
   float* fay_s = fax_s + TM;
-  float* cen = fay_s + TM;  // 1.0 for rows whose bound is finite, else 0.0
+  unsigned char* cen = reinterpret_cast<unsigned char*>(fay_s + TM);  // 1 for rows whose bound is finite, else 0
   // setup-only linearisation data lives in the scratch region
   double* a02 = scratch;      double* a12 = scratch + T;  double* Bm = scratch + 2 * T;  double* Cm = scratch + 8 * T;
   double* gam_b = scratch + 11 * T;
@@ -204,9 +205,9 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
     bool on = true;
     if (k < oRU) on = en_speed[(k % nU) & 1];
     else if (k < oDU) on = en_acce[((k - oRU) % nR) & 1];
-    cen[k] = on ? 1.0f : 0.0f;
+    cen[k] = on ? 1 : 0;
   }
-  auto enabled = [&](int k) -> bool { return cen[k] != 0.0f; };
+  auto enabled = [&](int k) -> bool { return cen[k] != 0; };
   int m_active = 2 * TD + 2 * TM;
   for (int c = 0; c < 2; ++c) m_active += (en_speed[c] ? 2 * T : 0) + (en_acce[c] ? 2 * (T - 1) : 0);
   const double inv_m = 1.0 / (double)(m_active > 0 ? m_active : 1);
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
       } else if (t > tj) {
         fx += a02[t] * fth; fy += a12[t] * fth;
       }
-      F[(0 * T + t) * nU + j] = fx; F[(1 * T + t) * nU + j] = fy; F[(2 * T + t) * nU + j] = fth;
+      if (t >= tj) { F[t * (t + 1) + j] = fx; F[FT + t * (t + 1) + j] = fy; F[2 * FT + t * (t + 1) + j] = fth; }
     }
   }
   __syncwarp();
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
       for (int r = 0; r < 3; ++r) {
         const double ga = (double)__fmul_rn(prm.q[r], rs[r * T1 + t + 1]);  // q_s * ref_s in float32
         const double g = 2.0 * qq[r] * ga + prm.bk * (double)ns[r * T1 + t + 1];
-        acc += F[(r * T + t) * nU + j] * (qd[r] * s0[r * T + t] - g);
+        acc += F[r * FT + t * (t + 1) + j] * (qd[r] * s0[r * T + t] - g);
       }
     if ((j & 1) == 0) acc += -2.0 * pu * gam_b[j >> 1];
     cv[j] = acc;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
     const int i = ptab[p] >> 8, j = ptab[p] & 255;
     double acc = 0;
     for (int t = i >> 1; t < T; ++t)
-      for (int r = 0; r < 3; ++r) acc += qd[r] * F[(r * T + t) * nU + i] * F[(r * T + t) * nU + j];
+      for (int r = 0; r < 3; ++r) acc += qd[r] * F[r * FT + t * (t + 1) + i] * F[r * FT + t * (t + 1) + j];
     if (i == j && (i & 1) == 0) acc += 2.0 * pu * pu;
     Hc[p] = acc;
   }
@@ -396,10 +397,10 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
         if (i >= 2) acc += cz[oRU + i - 2] - cz[oRL + i - 2];
         if (i < nR) acc -= cz[oRU + i] - cz[oRL + i];
         if (TD > 0) {
-          const double* fxp = F + (i >> 1) * nU + i;
-          const double* fyp = fxp + T * nU;
+          const double* fxp = F + (i >> 1) * ((i >> 1) + 1) + i;
+          const double* fyp = fxp + FT;
 #pragma unroll 2
-          for (int t = i >> 1; t < T; ++t, fxp += nU, fyp += nU) acc -= fxp[0] * e0[t] + fyp[0] * e1[t];
+          for (int t = i >> 1; t < T; ++t) { acc -= fxp[0] * e0[t] + fyp[0] * e1[t]; fxp += 2 * (t + 1); fyp += 2 * (t + 1); }
         }
         rdU[i] = acc;
         res = fmax(res, fabs(acc));
@@ -448,15 +449,13 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
       __syncwarp();
       if (TD > 0) {
         NB_LL(j, nU) {
-          const double* fxp = F + (j >> 1) * nU + j;
-          const double* fyp = fxp + T * nU;
-          double* gxp = Gx + (j >> 1) * nU + j;
-          double* gyp = gxp + T * nU;
+          int o = (j >> 1) * ((j >> 1) + 1) + j;
 #pragma unroll 2
-          for (int t = j >> 1; t < T; ++t, fxp += nU, fyp += nU, gxp += nU, gyp += nU) {
-            const double fx = fxp[0], fy = fyp[0];
-            gxp[0] = N00[t] * fx + N01[t] * fy;
-            gyp[0] = N01[t] * fx + N11[t] * fy;
+          for (int t = j >> 1; t < T; ++t) {
+            const double fx = F[o], fy = F[FT + o];
+            Gx[o] = N00[t] * fx + N01[t] * fy;
+            Gy[o] = N01[t] * fx + N11[t] * fy;
+            o += 2 * (t + 1);
           }
         }
         __syncwarp();
@@ -466,12 +465,12 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
         const int i = ptab[p] >> 8, j = ptab[p] & 255;
         double acc = Hc[p];
         if (TD > 0) {
-          const double* fxp = F + (i >> 1) * nU + i;
-          const double* fyp = fxp + T * nU;
-          const double* gxp = Gx + (i >> 1) * nU + j;
-          const double* gyp = gxp + T * nU;
+          int o = (i >> 1) * ((i >> 1) + 1);  // row t = i/2 of the packed layout; j <= i < 2(t+1) so both columns exist
 #pragma unroll 2
-          for (int t = i >> 1; t < T; ++t, fxp += nU, fyp += nU, gxp += nU, gyp += nU) acc += fxp[0] * gxp[0] + fyp[0] * gyp[0];
+          for (int t = i >> 1; t < T; ++t) {
+            acc += F[o + i] * Gx[o + j] + F[FT + o + i] * Gy[o + j];
+            o += 2 * (t + 1);
+          }
         }
         if (i == j) {
           acc += cz[oBU + i] * (double)cis[oBU + i] + cz[oBL + i] * (double)cis[oBL + i];
@@ -561,10 +560,10 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
             if (i >= 2) acc -= cdz[oRU + i - 2] * (double)cis[oRU + i - 2] - cdz[oRL + i - 2] * (double)cis[oRL + i - 2];
             if (i < nR) acc += cdz[oRU + i] * (double)cis[oRU + i] - cdz[oRL + i] * (double)cis[oRL + i];
             if (TD > 0) {
-              const double* fxp = F + (i >> 1) * nU + i;
-              const double* fyp = fxp + T * nU;
+              const double* fxp = F + (i >> 1) * ((i >> 1) + 1) + i;
+              const double* fyp = fxp + FT;
 #pragma unroll 2
-              for (int t = i >> 1; t < T; ++t, fxp += nU, fyp += nU) acc += fxp[0] * e0[t] + fyp[0] * e1[t];
+              for (int t = i >> 1; t < T; ++t) { acc += fxp[0] * e0[t] + fyp[0] * e1[t]; fxp += 2 * (t + 1); fyp += 2 * (t + 1); }
             }
             if (sl == 0) r0 = acc; else r1 = acc;
           }
@@ -607,8 +606,8 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
         __syncwarp();
         NB_LL(t, TD) {
           double ax = 0, ay = 0;
-          const double* fxp = F + t * nU;
-          const double* fyp = fxp + T * nU;
+          const double* fxp = F + t * (t + 1);
+          const double* fyp = fxp + FT;
 #pragma unroll 2
           for (int i = 0; i < 2 * (t + 1); ++i) {
             ax += fxp[i] * dU[i];
@@ -701,7 +700,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
   NB_LL(t, T) {
     double sx = s0[t], sy = s0[T + t], sth = s0[2 * T + t];
     for (int i = 0; i < 2 * (t + 1); ++i) {
-      sx += F[(0 * T + t) * nU + i] * x[i]; sy += F[(1 * T + t) * nU + i] * x[i]; sth += F[(2 * T + t) * nU + i] * x[i];
+      sx += F[t * (t + 1) + i] * x[i]; sy += F[FT + t * (t + 1) + i] * x[i]; sth += F[2 * FT + t * (t + 1) + i] * x[i];
     }
     if (keep_nominal) { sx = ns[t + 1]; sy = ns[T1 + t + 1]; sth = ns[2 * T1 + t + 1]; }
     // stash (H is dead) so that every read of nom_s is complete before any write (out may alias nom)
