@@ -181,7 +181,7 @@ def run_ours(args):
     dsets = [{k: (None if v is None else v.to(dev)) for k, v in s.items()} for s in sets]
     hsets = [{k: (None if v is None else v.pin_memory()) for k, v in s.items()} for s in sets]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    pan = make_pan(cfg, K=K, iter_threshold=0.0, max_envs=B, overlap=args.overlap)
+    pan = make_pan(cfg, K=K, iter_threshold=0.0, max_envs=B, overlap=args.overlap, dune_kernel=args.dune_kernel)
     lib = _lib.load()
     per_env = 3 * (T + 1) + 2 * T + T + 1
     packed = torch.empty(B, per_env, device=dev)
@@ -321,6 +321,7 @@ def main():
     ap.add_argument("--workload", default="C4")
     ap.add_argument("--envs", type=int, default=0, help="override B per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dune-kernel", type=int, default=1, help="NB_OPT_DUNE_KERNEL: 0 fp32 ffma, 1 mma.sync, 2 tcgen05")
     ap.add_argument("--overlap", type=int, default=1, help="env sub-batches pipelined on internal streams (NB_OPT_OVERLAP)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

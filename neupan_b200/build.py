@@ -57,6 +57,7 @@ def build(edge_dims=None, force: bool = False, verbose: bool = False) -> str:
     jobs = [([nvcc, *ARCH, *COMMON, *extra, f"-DNB_E={e}", "-c", os.path.join(CSRC, "dune_inst.cu"), "-o", os.path.join(OBJDIR, f"dune_e{e}.o")], f"dune E={e}")
             for e in edge_dims]
     jobs.append(([nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, "dune_mma.cu"), "-o", os.path.join(OBJDIR, "dune_mma.o")], "dune_mma"))
+    jobs.append(([nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, "dune_tc.cu"), "-o", os.path.join(OBJDIR, "dune_tc.o")], "dune_tc"))
     jobs.append(([nvcc, *ARCH, *COMMON, *extra, f"-DNB_EDGE_MASK={mask}", "-c", os.path.join(CSRC, "pan_api.cu"), "-o", os.path.join(OBJDIR, "pan_api.o")], "pan_api"))
 
     def run(job):
@@ -70,7 +71,7 @@ def build(edge_dims=None, force: bool = False, verbose: bool = False) -> str:
         for what, log in ex.map(run, jobs):
             if verbose:
                 print(f"--- {what}\n{log}")
-    objs = [os.path.join(OBJDIR, f"dune_e{e}.o") for e in edge_dims] + [os.path.join(OBJDIR, "dune_mma.o"), os.path.join(OBJDIR, "pan_api.o")]
+    objs = [os.path.join(OBJDIR, f"dune_e{e}.o") for e in edge_dims] + [os.path.join(OBJDIR, "dune_mma.o"), os.path.join(OBJDIR, "dune_tc.o"), os.path.join(OBJDIR, "pan_api.o")]
     r = subprocess.run([nvcc, *ARCH, "-shared", "-o", LIB, *objs], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -19,6 +19,9 @@ namespace nb {
 void build_mma_image(const float* w, int E, std::vector<unsigned char>& out);
 int launch_dune_mma(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, int cta_per_sm_limit, cudaStream_t st,
                     char* err, size_t errlen);
+// dune_tc.cu
+void build_tc_image(const float* w, int E, std::vector<unsigned char>& out);
+int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, cudaStream_t st, char* err, size_t errlen);
 }  // namespace nb
 
 namespace {
@@ -54,7 +57,8 @@ struct nb_pan {
   int max_smem_optin = 0;
   // device buffers
   float* d_weights = nullptr;
-  unsigned char* d_image = nullptr;  // fragment-ordered fp16 hi/lo weight image of the tensor-core DUNE kernel
+  unsigned char* d_image = nullptr;  // fragment-ordered fp16 hi/lo weight image of the mma.sync DUNE kernel
+  unsigned char* d_tc_image = nullptr;  // UMMA operand image of the tcgen05 DUNE kernel
   int dune_variant = 1;              // NB_OPT_DUNE_KERNEL: 0 = FP32 FFMA kernel, 1 = tensor-core kernel
   int overlap = 1;                   // NB_OPT_OVERLAP: number of env sub-batches pipelined on internal streams
   cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -91,6 +95,12 @@ int check_forward_args(const nb_pan* p, int B, int N) {
 int launch_dune(nb_pan* p, const nb::DuneParams& prm, cudaStream_t st, int cta_limit = 0) {
   int rc = NB_ERR_INVALID;
   char msg[256] = "";
+  if (p->dune_variant == 2) {
+    rc = nb::launch_dune_tc(prm, p->d_tc_image, p->sm_count, p->max_smem_optin, st, msg, sizeof(msg));
+    if (rc) return fail(rc, "%s", msg);
+    ++g_launches;
+    return NB_OK;
+  }
   if (p->dune_variant == 1) {
     rc = nb::launch_dune_mma(prm, p->d_image, p->sm_count, p->max_smem_optin, cta_limit, st, msg, sizeof(msg));
     if (rc) return fail(rc, "%s", msg);
@@ -243,6 +253,9 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
     nb::build_mma_image(weights, cfg->edge_dim, image);
     NB_CUDA(dalloc(&p->d_image, image.size()));
     NB_CUDA(cudaMemcpy(p->d_image, image.data(), image.size(), cudaMemcpyHostToDevice));
+    nb::build_tc_image(weights, cfg->edge_dim, image);
+    NB_CUDA(dalloc(&p->d_tc_image, image.size()));
+    NB_CUDA(cudaMemcpy(p->d_tc_image, image.data(), image.size(), cudaMemcpyHostToDevice));
   }
   NB_CUDA(dalloc(&p->sel_mu, B * T1 * M * E));
   NB_CUDA(dalloc(&p->sel_lam, B * T1 * M * 2));
@@ -276,7 +289,7 @@ int nb_pan_destroy(nb_pan_t* p) {
     if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
   }
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
-  void* bufs[] = {p->d_image, p->d_weights, p->sel_mu, p->sel_lam, p->sel_pts, p->sel_dist, p->sel_count, p->prev_s, p->prev_u, p->prev_mu,
+  void* bufs[] = {p->d_tc_image, p->d_image, p->d_weights, p->sel_mu, p->sel_lam, p->sel_pts, p->sel_dist, p->sel_count, p->prev_s, p->prev_u, p->prev_mu,
                   p->prev_lam, p->prev_count, p->prev_valid, p->active, p->iters, p->status, p->ipm_it, p->min_dist, p->h_in, p->h_out, p->h_np, p->h_io};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -300,7 +313,7 @@ int nb_pan_set_iteration(nb_pan_t* p, int32_t iter_num, float iter_threshold) {
 int nb_pan_set_option(nb_pan_t* p, int32_t option, int32_t value) {
   if (!p) return fail(NB_ERR_INVALID, "null handle");
   if (option == NB_OPT_DUNE_KERNEL) {
-    if (value != 0 && value != 1) return fail(NB_ERR_INVALID, "NB_OPT_DUNE_KERNEL takes 0 (fp32 ffma) or 1 (tensor core)");
+    if (value < 0 || value > 2) return fail(NB_ERR_INVALID, "NB_OPT_DUNE_KERNEL takes 0 (fp32 ffma), 1 (mma.sync) or 2 (tcgen05)");
     p->dune_variant = value;
     return NB_OK;
   }
