@@ -64,7 +64,7 @@ class PAN(torch.nn.Module):
         self.device = torch.device("cuda", dev.index if dev.index is not None else 0)
         self._handle = None
         self.overlap = int(kwargs.get("overlap", 1))  # env sub-batches pipelined on internal streams (1 = off)
-        self.dune_kernel = int(kwargs.get("dune_kernel", 1))  # 1 = tensor-core DUNE kernel, 0 = all-FP32 FFMA kernel
+        self.dune_kernel = int(kwargs.get("dune_kernel", 2))  # 2 = tcgen05 DUNE kernel (default), 1 = mma.sync, 0 = all-FP32 FFMA
         self._cap = (max(1, int(kwargs.get("max_envs", 1))), max(1, int(kwargs.get("max_points", max(1, dune_max_num)))))
         self._sent = None  # (adjust version, iter_num, iter_threshold) last pushed to the handle
         self._last = None  # bookkeeping of the last forward (for the lazy properties)

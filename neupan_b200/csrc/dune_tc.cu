@@ -1,5 +1,6 @@
 // Translation unit of the tcgen05 DUNE kernel: host-side operand image + launcher.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -22,35 +23,38 @@ void build_tc_image(const float* w, int E, std::vector<unsigned char>& out) {
   auto put = [&](size_t off, uint16_t v) { memcpy(out.data() + off, &v, 2); };
   // element (n, k) of a K-major operand with `lbo` bytes between the two 8-half K groups and `kstep` bytes per 16 of K
   auto at = [](int n, int k, int lbo, int kstep) { return (size_t)(k / 16) * kstep + ((k % 16) / 8) * lbo + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2; };
+  float* fl = reinterpret_cast<float*>(out.data() + I::kFloatOff);
   const int hidden_w[4] = {L::W3, L::W5, L::W8, L::W10}, hidden_b[4] = {L::B3, L::B5, L::B8, L::B10};
+  // layers fed by a tanh (MLP.3, MLP.8 and the head MLP.13) receive r = 1/(exp(2y)+1) instead of tanh(y) = 1 - 2r:
+  //   W tanh + b = (b + rowsum(W)) + (-2 W) r
+  const bool after_tanh[4] = {true, false, true, false};
   for (int l = 0; l < 4; ++l) {
     const size_t base = (size_t)l * I::kHiddenStride;
     for (int n = 0; n < 32; ++n) {
+      double rowsum = 0.0;
       for (int k = 0; k < 32; ++k) {
+        const float wv = w[hidden_w[l] + n * 32 + k];
+        rowsum += (double)wv;
         uint16_t hi, lo;
-        split_half_tc(w[hidden_w[l] + n * 32 + k], hi, lo);
+        split_half_tc(after_tanh[l] ? -2.0f * wv : wv, hi, lo);
         put(base + at(n, k, 512, 1024), hi);
         put(base + 2048 + at(n, k, 512, 1024), lo);
       }
-      uint16_t hi, lo;
-      split_half_tc(w[hidden_b[l] + n], hi, lo);
-      put(base + 4096 + at(n, 0, 512, 1024), hi);
-      put(base + 4096 + at(n, 1, 512, 1024), lo);
+      fl[I::BH + 32 * l + n] = (float)((double)w[hidden_b[l] + n] + (after_tanh[l] ? rowsum : 0.0));
     }
   }
-  for (int n = 0; n < E; ++n) {  // head, N padded to 16 with zero rows
+  for (int n = 0; n < E; ++n) {  // head (after a tanh), N padded to 16 with zero rows
+    double rowsum = 0.0;
     for (int k = 0; k < 32; ++k) {
+      const float wv = w[L::W13 + n * 32 + k];
+      rowsum += (double)wv;
       uint16_t hi, lo;
-      split_half_tc(w[L::W13 + n * 32 + k], hi, lo);
+      split_half_tc(-2.0f * wv, hi, lo);
       put(I::kHeadOff + at(n, k, 256, 512), hi);
       put(I::kHeadOff + 1024 + at(n, k, 256, 512), lo);
     }
-    uint16_t hi, lo;
-    split_half_tc(w[L::b13(E) + n], hi, lo);
-    put(I::kHeadOff + 2048 + at(n, 0, 256, 512), hi);
-    put(I::kHeadOff + 2048 + at(n, 1, 256, 512), lo);
+    fl[I::BHEAD + n] = (float)((double)w[L::b13(E) + n] + rowsum);
   }
-  float* fl = reinterpret_cast<float*>(out.data() + I::kFloatOff);
   memcpy(fl + I::W0, w + L::W0, 64 * 4);
   memcpy(fl + I::B0, w + L::B0, 32 * 4);
   const int g_src[3] = {L::G1, L::G6, L::G11}, b_src[3] = {L::BE1, L::BE6, L::BE11};
@@ -63,18 +67,31 @@ void build_tc_image(const float* w, int E, std::vector<unsigned char>& out) {
 }
 
 int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, cudaStream_t st, char* err, size_t errlen) {
-  const size_t smem = dune_tc_smem_bytes(prm.N, prm.geo.E, prm.M);
+  size_t smem = dune_tc_smem_bytes(prm.N, prm.geo.E, prm.M);
+  // Each CTA holds 64 of the SM's 512 TMEM columns for its whole (persistent) lifetime, so at most 8 CTAs may share an
+  // SM; a 9th would sit in tcgen05.alloc until another one exits, and the block scheduler knows nothing about TMEM.
+  // (Observed with 128 columns / CTA: a 5th CTA landing on an SM turned 2.7 ms into 4.3 ms per launch.)  Registers
+  // (96 x 128 threads) admit 5 CTAs; the shared-memory request is padded so that never more than 5 fit.
+  if (smem < 38 * 1024) smem = 38 * 1024;
   if ((long long)smem > max_smem_optin) {
     snprintf(err, errlen, "N=%d needs %zu B of shared memory (limit %d)", prm.N, smem, max_smem_optin);
     return -3;
   }
   const int items = prm.B * (prm.T + 1);
   cudaError_t e = cudaFuncSetAttribute(dune_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int per_sm = 1;
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dune_tc_kernel, 128, smem);
+  cudaFuncAttributes fa{};
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, dune_tc_kernel);
   if (e == cudaSuccess) {
+    // resident CTAs per SM: registers, shared memory (1 KB reserved per CTA) and 512 TMEM columns / 128 per CTA.
+    // (cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for this kernel; ncu's limits say 5.)
+    int by_regs = 65536 / ((fa.numRegs > 0 ? fa.numRegs : 128) * 128);
+    int by_smem = (int)(233472 / (smem + fa.sharedSizeBytes + 1024));
+    int per_sm = by_regs < by_smem ? by_regs : by_smem;
+    if (per_sm > 5) per_sm = 5;
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;  // 4 x 128 TMEM columns per SM
+    static int dbg = -1;
+    if (dbg < 0) dbg = getenv("NB_DEBUG") ? 1 : 0;
+    if (dbg) fprintf(stderr, "[nb] dune_tc: regs %d, smem %zu + %zu, per_sm %d\n", fa.numRegs, smem, (size_t)fa.sharedSizeBytes, per_sm);
     int grid = sm_count * per_sm;
     if (grid > items) grid = items;
     dune_tc_kernel<<<grid, 128, smem, st>>>(prm, d_image);

@@ -4,13 +4,13 @@
 // thread r owns point r of a 128-point tile for the whole network, so LayerNorm statistics, tanh, ReLU
 // and the distance are thread-local (no shuffles, no fragment bookkeeping).  Per dense layer:
 //   registers --split x = hi + lo (fp16)--> tcgen05.st (A operand, TMEM)         [all threads]
-//   D[128 x 32] = [1 1 0..] . B_bias  +  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi        [one thread, tcgen05.mma,
+//   D[128 x 32] = bias (tcgen05.st) + A_lo.B_hi + A_hi.B_lo + A_hi.B_hi           [one thread, tcgen05.mma,
 //                                                               B from shared memory via UMMA descriptors]
 //   tcgen05.commit -> mbarrier -> tcgen05.ld (32 fp32 columns = the thread's row)  [all threads]
-// The bias rides on one extra K=16 MMA whose A operand is the constant row [1, 1, 0, ...] (b = b_hi + b_lo).
 // Layouts / descriptors were verified in isolation with tools/tc05_probe.cu.
 //
-// TMEM columns per CTA (128 allocated): D [0,32)  A_hi [32,48)  A_lo [48,64)  A_one [64,72).
+// TMEM columns per CTA (64 allocated): D [0,32)  A_hi [32,48)  A_lo [48,64).  D is pre-loaded with the bias row by
+// tcgen05.st (every thread writes the same 32 floats into its lane), all MMAs then accumulate.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -22,12 +22,14 @@ namespace nb {
 // Weight image built on the host (dune_tc.cu): canonical K-major / no-swizzle UMMA operand layout
 // (core matrix = 8 rows x 16 B; SBO = 128 B between 8-row groups; LBO between the two 8-half K groups).
 struct TcImage {
-  static constexpr int kHiddenStride = 5120;         // per hidden layer: W_hi 2048 | W_lo 2048 | bias 1024
-  static constexpr int kHeadOff = 4 * kHiddenStride;  // head (N padded to 16): W_hi 1024 | W_lo 1024 | bias 512
-  static constexpr int kFloatOff = kHeadOff + 2560;   // 23040
-  // float section (offsets in floats): W0 (32x2), b0, then LayerNorm gain/offset pre-multiplied by 2*log2(e)
-  static constexpr int W0 = 0, B0 = 64, G1 = 96, BE1 = 128, G6 = 160, BE6 = 192, G11 = 224, BE11 = 256, kFloats = 288;
-  static constexpr int kBytes = kFloatOff + kFloats * 4;  // 24192
+  static constexpr int kHiddenStride = 4096;         // per hidden layer: W_hi 2048 | W_lo 2048
+  static constexpr int kHeadOff = 4 * kHiddenStride;  // head (N padded to 16): W_hi 1024 | W_lo 1024
+  static constexpr int kFloatOff = kHeadOff + 2048;   // 18432
+  // float section (offsets in floats): W0 (32x2), b0, LayerNorm gain/offset pre-multiplied by 2*log2(e), then the
+  // biases of the four hidden layers and of the head (16, zero padded) -- already including the folded tanh map
+  static constexpr int W0 = 0, B0 = 64, G1 = 96, BE1 = 128, G6 = 160, BE6 = 192, G11 = 224, BE11 = 256, BH = 288, BHEAD = 416,
+                       kFloats = 432;
+  static constexpr int kBytes = kFloatOff + kFloats * 4;  // 20160
 };
 
 namespace tc {
@@ -68,6 +70,32 @@ __device__ __forceinline__ void st16(uint32_t taddr, const uint32_t (&a)[16]) {
                : "memory");
 }
 
+// every thread writes the same 32-float row (the layer's bias) into its TMEM lane: D := bias
+__device__ __forceinline__ void st_bias32(uint32_t taddr, const float* __restrict__ b) {
+  uint32_t v[32];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const uint4 q = *reinterpret_cast<const uint4*>(b + 4 * j4);
+    v[4 * j4] = q.x; v[4 * j4 + 1] = q.y; v[4 * j4 + 2] = q.z; v[4 * j4 + 3] = q.w;
+  }
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]),
+      "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
+      "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void st_bias16(uint32_t taddr, const float* __restrict__ b) {
+  uint32_t v[16];
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const uint4 q = *reinterpret_cast<const uint4*>(b + 4 * j4);
+    v[4 * j4] = q.x; v[4 * j4 + 1] = q.y; v[4 * j4 + 2] = q.z; v[4 * j4 + 3] = q.w;
+  }
+  st16(taddr, v);
+}
+
 __device__ __forceinline__ void ld32(uint32_t taddr, float (&h)[32]) {
   uint32_t d[32];
   asm volatile(
@@ -106,12 +134,14 @@ __device__ __forceinline__ void split32(const float (&h)[32], uint32_t (&hi)[16]
   }
 }
 
-__device__ __forceinline__ float tanh_scaled(float a) {  // tanh(y) with a = 2*log2(e)*y
+// r = 1/(exp2(a) + 1) with a = 2*log2(e)*y; tanh(y) = 1 - 2r.  The affine map 1 - 2r is folded into the weights and
+// bias of the layer that follows (W' = -2W, b' = b + rowsum(W), built on the host), so r itself is the activation.
+__device__ __forceinline__ float tanh_r(float a) {
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
   const float d = e + 1.0f;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-  return fmaf(-2.0f, r, 1.0f);
+  return r;
 }
 
 // thread-local LayerNorm (eps 1e-5, biased variance) + tanh; g / be pre-scaled by 2*log2(e)
@@ -131,24 +161,23 @@ __device__ __forceinline__ void ln_tanh32(float (&h)[32], const float* __restric
   for (int j4 = 0; j4 < 8; ++j4) {
     const float4 gg = *reinterpret_cast<const float4*>(g + 4 * j4);
     const float4 bb = *reinterpret_cast<const float4*>(be + 4 * j4);
-    h[4 * j4 + 0] = tanh_scaled(fmaf(h[4 * j4 + 0] * r, gg.x, bb.x));
-    h[4 * j4 + 1] = tanh_scaled(fmaf(h[4 * j4 + 1] * r, gg.y, bb.y));
-    h[4 * j4 + 2] = tanh_scaled(fmaf(h[4 * j4 + 2] * r, gg.z, bb.z));
-    h[4 * j4 + 3] = tanh_scaled(fmaf(h[4 * j4 + 3] * r, gg.w, bb.w));
+    h[4 * j4 + 0] = tanh_r(fmaf(h[4 * j4 + 0] * r, gg.x, bb.x));
+    h[4 * j4 + 1] = tanh_r(fmaf(h[4 * j4 + 1] * r, gg.y, bb.y));
+    h[4 * j4 + 2] = tanh_r(fmaf(h[4 * j4 + 2] * r, gg.z, bb.z));
+    h[4 * j4 + 3] = tanh_r(fmaf(h[4 * j4 + 3] * r, gg.w, bb.w));
   }
 }
 
 }  // namespace tc
 
 __host__ __device__ inline size_t dune_tc_smem_bytes(int N, int E, int M) {
-  return 128 + TcImage::kBytes + (size_t)N * 8 + (((size_t)N * E * 4 + 7) / 8) * 8 + (size_t)4 * M * 8 + 64;
+  return TcImage::kBytes + (size_t)N * 8 + (((size_t)N * E * 4 + 7) / 8) * 8 + (size_t)4 * M * 8 + 64;
 }
 
-__global__ void __launch_bounds__(128, 4) dune_tc_kernel(const DuneParams prm, const unsigned char* __restrict__ image) {
-  extern __shared__ __align__(128) unsigned char smem_dyn[];
+__global__ void __launch_bounds__(128, 5) dune_tc_kernel(const DuneParams prm, const unsigned char* __restrict__ image) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];  // the attribute aligns the dynamic segment (UMMA operands need 128 B)
   using I = TcImage;
-  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
-  unsigned char* simg = base;  // 128-B aligned operand image
+  unsigned char* simg = smem_dyn;  // operand image
   const float* fl = reinterpret_cast<const float*>(simg + I::kFloatOff);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(simg + I::kBytes);
   float* smu = reinterpret_cast<float*>(simg + I::kBytes + (size_t)prm.N * 8);
@@ -164,7 +193,7 @@ __global__ void __launch_bounds__(128, 4) dune_tc_kernel(const DuneParams prm, c
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand image -> visible to the tensor core (async proxy)
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(tc::smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(tc::smem_u32(&tmem_base_s)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -172,16 +201,7 @@ __global__ void __launch_bounds__(128, 4) dune_tc_kernel(const DuneParams prm, c
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tbase = tmem_base_s;
   const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
-  const uint32_t tD = tbase, tAhi = tbase + 32, tAlo = tbase + 48, tAone = tbase + 64;
-  {  // constant A operand of the bias MMA: row = [1, 1, 0, ..., 0]
-    uint32_t one[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) one[c] = 0u;
-    const __half2 h11 = __floats2half2_rn(1.0f, 1.0f);
-    one[0] = *reinterpret_cast<const uint32_t*>(&h11);
-    tc::st16(trow + 64, one);  // columns 64..79 (only 64..71 are read)
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-  }
+  const uint32_t tD = tbase, tAhi = tbase + 32, tAlo = tbase + 48;
   const uint32_t simg_u = tc::smem_u32(simg);
   const uint32_t bar = tc::smem_u32(&mbar);
   uint32_t phase = 0;
@@ -192,13 +212,13 @@ __global__ void __launch_bounds__(128, 4) dune_tc_kernel(const DuneParams prm, c
     tc::split32(h, hi, lo);
     tc::st16(trow + 32, hi);
     tc::st16(trow + 48, lo);
+    tc::st_bias32(trow, fl + I::BH + 32 * layer);  // D := bias; every MMA below accumulates
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t w = simg_u + layer * I::kHiddenStride;
-      tc::mma_f16(tD, tAone, tc::b_desc(w + 4096, 512), tc::kIdescN32, 0u);  // bias (also clears D)
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const uint64_t bhi = tc::b_desc(w + s * 1024, 512), blo = tc::b_desc(w + 2048 + s * 1024, 512);
@@ -218,13 +238,13 @@ __global__ void __launch_bounds__(128, 4) dune_tc_kernel(const DuneParams prm, c
     tc::split32(h, hi, lo);
     tc::st16(trow + 32, hi);
     tc::st16(trow + 48, lo);
+    tc::st_bias16(trow, fl + I::BHEAD);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t w = simg_u + I::kHeadOff;
-      tc::mma_f16(tD, tAone, tc::b_desc(w + 2048, 256), tc::kIdescN16, 0u);
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const uint64_t bhi = tc::b_desc(w + s * 512, 256), blo = tc::b_desc(w + 1024 + s * 512, 256);
@@ -375,7 +395,7 @@ __global__ void __launch_bounds__(128, 4) dune_tc_kernel(const DuneParams prm, c
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tbase) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tbase) : "memory");
 }
 
 }  // namespace nb

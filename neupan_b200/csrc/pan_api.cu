@@ -59,7 +59,7 @@ struct nb_pan {
   float* d_weights = nullptr;
   unsigned char* d_image = nullptr;  // fragment-ordered fp16 hi/lo weight image of the mma.sync DUNE kernel
   unsigned char* d_tc_image = nullptr;  // UMMA operand image of the tcgen05 DUNE kernel
-  int dune_variant = 1;              // NB_OPT_DUNE_KERNEL: 0 = FP32 FFMA kernel, 1 = tensor-core kernel
+  int dune_variant = 2;              // NB_OPT_DUNE_KERNEL: 0 = FP32 FFMA, 1 = mma.sync tensor-core, 2 = tcgen05 tensor-core kernel
   int overlap = 1;                   // NB_OPT_OVERLAP: number of env sub-batches pipelined on internal streams
   cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};

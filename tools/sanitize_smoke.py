@@ -8,7 +8,7 @@ from helpers import CONFIGS, make_inputs
 for cname, B, N in (("C4", 6, 70), ("C5", 3, 40), ("C2", 5, 33)):
     cfg = CONFIGS[cname]
     inp = make_inputs(cfg, B=B, N=N, scene="obstacles")
-    for dk in (1, 0):
+    for dk in (2, 1, 0):
         pan = make_pan(cfg, K=2, N=N, max_envs=B, dune_kernel=dk)
         S, U, D, md = run_pan(pan, inp)
         assert np.isfinite(S).all() and (pan.status.cpu().numpy() == 0).all()
