@@ -68,37 +68,42 @@ void build_tc_image(const float* w, int E, std::vector<unsigned char>& out) {
 
 int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, cudaStream_t st, char* err, size_t errlen) {
   size_t smem = dune_tc_smem_bytes(prm.N, prm.geo.E, prm.M);
-  // Each CTA holds 64 of the SM's 512 TMEM columns for its whole (persistent) lifetime, so at most 8 CTAs may share an
-  // SM; a 9th would sit in tcgen05.alloc until another one exits, and the block scheduler knows nothing about TMEM.
-  // (Observed with 128 columns / CTA: a 5th CTA landing on an SM turned 2.7 ms into 4.3 ms per launch.)  Registers
-  // (96 x 128 threads) admit 5 CTAs; the shared-memory request is padded so that never more than 5 fit.
-  if (smem < 38 * 1024) smem = 38 * 1024;
   if ((long long)smem > max_smem_optin) {
     snprintf(err, errlen, "N=%d needs %zu B of shared memory (limit %d)", prm.N, smem, max_smem_optin);
     return -3;
   }
   const int items = prm.B * (prm.T + 1);
-  cudaError_t e = cudaFuncSetAttribute(dune_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncAttributes fa{};
-  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, dune_tc_kernel);
+  static int force = -1;  // NB_DUNE_TC: developer switch, 1 = single-slot kernel, 2 = ping-pong kernel
+  if (force < 0) {
+    const char* v = getenv("NB_DUNE_TC");
+    force = v ? atoi(v) : 0;
+  }
+  // The single-slot kernel with 5 CTAs per SM is the default: measured 2.49 ms per launch at C4 against 3.14 ms for the
+  // ping-pong kernel (two tiles in flight per CTA + issuer warp; its polling issuer and 4-CTA limit cost more than the
+  // intra-CTA overlap gains).  NB_DUNE_TC=2 selects the ping-pong kernel for experiments.
+  const bool pingpong = force == 2;
+  // TMEM columns are held by a CTA for its whole (persistent) lifetime: 512 / columns-per-CTA CTAs may share an SM, one
+  // more would sit in tcgen05.alloc until another CTA exits, and the block scheduler knows nothing about TMEM
+  // (observed: a 5th CTA with 128 columns landing on an SM turned 2.7 ms into 4.3 ms per launch).  The shared-memory
+  // request is therefore padded so that never more CTAs fit than registers and TMEM admit.
+  const int threads = pingpong ? 160 : 128;
+  const int want = pingpong ? 4 : 5;  // ping-pong: 128 columns -> 4 CTAs;  single slot: 64 columns, 96 registers -> 5 CTAs
+  const size_t pad = (size_t)(233472 / want) - 1024 - 1024;  // just small enough that `want` CTAs fit, want + 1 do not
+  if (smem < pad) smem = pad;
+  cudaError_t e = pingpong ? cudaFuncSetAttribute(dune_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(dune_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) {
-    // resident CTAs per SM: registers, shared memory (1 KB reserved per CTA) and 512 TMEM columns / 128 per CTA.
-    // (cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for this kernel; ncu's limits say 5.)
-    int by_regs = 65536 / ((fa.numRegs > 0 ? fa.numRegs : 128) * 128);
-    int by_smem = (int)(233472 / (smem + fa.sharedSizeBytes + 1024));
-    int per_sm = by_regs < by_smem ? by_regs : by_smem;
-    if (per_sm > 5) per_sm = 5;
+    int per_sm = (int)(233472 / (smem + 2048));
+    if (per_sm > want) per_sm = want;
     if (per_sm < 1) per_sm = 1;
-    static int dbg = -1;
-    if (dbg < 0) dbg = getenv("NB_DEBUG") ? 1 : 0;
-    if (dbg) fprintf(stderr, "[nb] dune_tc: regs %d, smem %zu + %zu, per_sm %d\n", fa.numRegs, smem, (size_t)fa.sharedSizeBytes, per_sm);
     int grid = sm_count * per_sm;
     if (grid > items) grid = items;
-    dune_tc_kernel<<<grid, 128, smem, st>>>(prm, d_image);
+    if (pingpong) dune_tc2_kernel<<<grid, threads, smem, st>>>(prm, d_image);
+    else dune_tc_kernel<<<grid, threads, smem, st>>>(prm, d_image);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {
-    snprintf(err, errlen, "dune_tc_kernel launch failed: %s", cudaGetErrorString(e));
+    snprintf(err, errlen, "dune_tc kernel launch failed: %s", cudaGetErrorString(e));
     return -2;
   }
   return 0;

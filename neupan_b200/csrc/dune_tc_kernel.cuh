@@ -54,9 +54,11 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint32_t a_tmem, uint64
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (int i = 0; i < (1 << 26); ++i) {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+    // the suspend-time hint lets the hardware park the thread until the phase completes (or the time limit passes)
+    // instead of returning immediately: fewer polling instructions competing for issue slots
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok)
-                 : "r"(bar), "r"(parity)
+                 : "r"(bar), "r"(parity), "r"(20000u)
                  : "memory");
     if (ok) return;
   }
@@ -396,6 +398,268 @@ __global__ void __launch_bounds__(128, 5) dune_tc_kernel(const DuneParams prm, c
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tbase) : "memory");
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// Ping-pong version: two 128-point tiles in flight per CTA and a dedicated MMA-issuer warp.
+//   warps 0-3 (compute): thread r owns point r of tile A (TMEM slot 0) and of tile B (slot 1) and alternates
+//     between them: wait D[slot] -> tcgen05.ld -> epilogue (LN/tanh/ReLU/split) -> tcgen05.st A[slot] + bias ->
+//     arrive on a_ready[slot].  While it works on one slot the tensor core computes the other, so the waits are
+//     (almost) always already satisfied and no block-wide barrier is needed inside the tile loop.
+//   warp 4 (issuer): wait a_ready[slot] (4 arrivals, one per compute warp) -> 6 tcgen05.mma -> tcgen05.commit -> d_ready[slot].
+// TMEM per CTA: 128 columns = 2 slots x {D [0,32) | A_hi [32,48) | A_lo [48,64)}.
+__host__ __device__ inline size_t dune_tc2_smem_bytes(int N, int E, int M) { return dune_tc_smem_bytes(N, E, M); }
+
+__global__ void __launch_bounds__(160, 4) dune_tc2_kernel(const DuneParams prm, const unsigned char* __restrict__ image) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  using I = TcImage;
+  unsigned char* simg = smem_dyn;
+  const float* fl = reinterpret_cast<const float*>(simg + I::kFloatOff);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(simg + I::kBytes);
+  float* smu = reinterpret_cast<float*>(simg + I::kBytes + (size_t)prm.N * 8);
+  unsigned long long* cands = reinterpret_cast<unsigned long long*>(simg + I::kBytes + (size_t)prm.N * 8 + (((size_t)prm.N * prm.geo.E * 4 + 7) / 8) * 8);
+  __shared__ __align__(8) unsigned long long a_ready[2], d_ready[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool issuer = warp == 4;
+  for (int i = tid; i < I::kBytes / 16; i += 160) reinterpret_cast<uint4*>(simg)[i] = reinterpret_cast<const uint4*>(image)[i];
+  if (tid == 0) {
+    for (int sl = 0; sl < 2; ++sl) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(tc::smem_u32(&a_ready[sl])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(&d_ready[sl])));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(tc::smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t simg_u = tc::smem_u32(simg);
+  uint32_t ph[2] = {0u, 0u};  // compute warps: parity of d_ready[slot]; issuer: parity of a_ready[slot]
+
+  const int T1 = prm.T + 1, N = prm.N, M = prm.M, E = prm.geo.E;
+  const int items = prm.B * T1;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / T1, t = item - b * T1;
+    if (prm.active && prm.active[b] == 0) continue;  // uniform per CTA
+    int n = prm.num_points ? prm.num_points[b] : N;
+    n = n < 0 ? 0 : (n > N ? N : n);
+    const int cnt = n < M ? n : M;
+    if (t == 0 && tid == 0) {
+      prm.sel_count[b] = cnt;
+      if (n == 0 && prm.min_dist) prm.min_dist[b] = __int_as_float(0x7f800000);
+    }
+    if (n == 0) continue;
+    const int pairs = (n + 255) >> 8;  // two tiles of 128 points per pass
+
+    if (issuer) {
+      // ---- MMA issuer warp ---------------------------------------------------------------------------
+#pragma unroll 1
+      for (int pr = 0; pr < pairs; ++pr)
+#pragma unroll 1
+        for (int st = 0; st < 5; ++st)
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            tc::mbar_wait(tc::smem_u32(&a_ready[sl]), ph[sl]);
+            ph[sl] ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+              const uint32_t tD = tbase + 64 * sl, tAhi = tD + 32, tAlo = tD + 48;
+              const bool is_head = st == 4;
+              const uint32_t w = simg_u + (is_head ? I::kHeadOff : st * I::kHiddenStride);
+              const uint32_t lbo = is_head ? 256u : 512u, ks = is_head ? 512u : 1024u, lo_off = is_head ? 1024u : 2048u;
+              const uint32_t idesc = is_head ? tc::kIdescN16 : tc::kIdescN32;
+#pragma unroll
+              for (int s = 0; s < 2; ++s) {
+                const uint64_t bhi = tc::b_desc(w + s * ks, lbo), blo = tc::b_desc(w + lo_off + s * ks, lbo);
+                tc::mma_f16(tD, tAlo + 8 * s, bhi, idesc, 1u);
+                tc::mma_f16(tD, tAhi + 8 * s, blo, idesc, 1u);
+                tc::mma_f16(tD, tAhi + 8 * s, bhi, idesc, 1u);
+              }
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(&d_ready[sl])) : "memory");
+            }
+            __syncwarp();
+          }
+    } else {
+      // ---- compute warps -----------------------------------------------------------------------------
+      const float* ns = prm.nom_s + (size_t)b * 3 * T1;
+      const float sx = ns[t], sy = ns[T1 + t], th = ns[2 * T1 + t];
+      const float cs = cosf(th), sn = sinf(th);
+      const float* px = prm.points + (size_t)b * 2 * N;
+      const float* py = px + N;
+      const float* vx = prm.velocities ? prm.velocities + (size_t)b * 2 * N : nullptr;
+      const float* vy = vx ? vx + N : nullptr;
+      const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
+
+      // hand the activations h of one slot to the tensor core: A := split(h), D := bias, signal the issuer
+      auto publish = [&](const float (&h)[32], int sl, const float* bias, bool head) {
+        uint32_t hi[16], lo[16];
+        tc::split32(h, hi, lo);
+        tc::st16(trow + 64 * sl + 32, hi);
+        tc::st16(trow + 64 * sl + 48, lo);
+        if (head) tc::st_bias16(trow + 64 * sl, bias); else tc::st_bias32(trow + 64 * sl, bias);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&a_ready[sl])) : "memory");
+      };
+      auto acquire = [&](int sl) {
+        tc::mbar_wait(tc::smem_u32(&d_ready[sl]), ph[sl]);
+        ph[sl] ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      };
+
+#pragma unroll 1
+      for (int pr = 0; pr < pairs; ++pr) {
+        float x0[2], y0[2];
+        int pi[2];
+        bool valid[2];
+        // stage 0 of both slots: layer 0 + LayerNorm/tanh on the FMA / MUFU pipes
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          int i = (pr * 2 + sl) * 128 + tid;
+          valid[sl] = i < n;
+          i = valid[sl] ? i : n - 1;
+          pi[sl] = i;
+          float gx = px[i], gy = py[i];
+          if (vx) {
+            gx = flow(gx, vx[i], prm.dt, t);
+            gy = flow(gy, vy[i], prm.dt, t);
+          }
+          const float dx = gx - sx, dy = gy - sy;
+          x0[sl] = fmaf(cs, dx, sn * dy);
+          y0[sl] = fmaf(cs, dy, -(sn * dx));
+          float h[32];
+#pragma unroll
+          for (int j2 = 0; j2 < 16; ++j2) {
+            const float4 w = *reinterpret_cast<const float4*>(fl + I::W0 + 4 * j2);
+            const float2 bb = *reinterpret_cast<const float2*>(fl + I::B0 + 2 * j2);
+            h[2 * j2] = fmaf(w.y, y0[sl], fmaf(w.x, x0[sl], bb.x));
+            h[2 * j2 + 1] = fmaf(w.w, y0[sl], fmaf(w.z, x0[sl], bb.y));
+          }
+          tc::ln_tanh32(h, fl + I::G1, fl + I::BE1);
+          publish(h, sl, fl + I::BH, false);
+        }
+        // stages 1..4: epilogue of dense layer st-1, input of dense layer st (st == 4: the head)
+#pragma unroll 1
+        for (int st = 1; st < 5; ++st) {
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            float h[32];
+            acquire(sl);
+            tc::ld32(trow + 64 * sl, h);
+            if (st == 1 || st == 3) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j], 0.f);
+            } else if (st == 2) {
+              tc::ln_tanh32(h, fl + I::G6, fl + I::BE6);
+            } else {
+              tc::ln_tanh32(h, fl + I::G11, fl + I::BE11);
+            }
+            publish(h, sl, st == 4 ? fl + I::BHEAD : fl + I::BH + 32 * st, st == 4);
+          }
+        }
+        // head epilogue: mu = relu(.), distance, key
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          float mu[8];
+          acquire(sl);
+          tc::ld8(trow + 64 * sl, mu);
+          float d = 0.f;
+#pragma unroll
+          for (int e = 0; e < kMaxEdges; ++e) {
+            if (e < E) {
+              mu[e] = fmaxf(mu[e], 0.f);
+              const float ge = fmaf(prm.geo.G[e][1], y0[sl], prm.geo.G[e][0] * x0[sl]) - prm.geo.h[e];
+              d = fmaf(mu[e], ge, d);
+              if (valid[sl]) smu[pi[sl] * E + e] = mu[e];
+            }
+          }
+          if (valid[sl]) keys[pi[sl]] = ((unsigned long long)orderable(d) << 32) | (unsigned)pi[sl];
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- top-M (compute warps; the issuer warp only joins the barriers) ---------------------------------
+    unsigned long long mine = ~0ull;
+    if (!issuer) {
+      unsigned long long* cand = cands + warp * M;
+      for (int m = 0; m < cnt; ++m) {
+        unsigned bd = 0xFFFFFFFFu, bi = 0xFFFFFFFFu;
+        for (int i = warp * 32 + lane; i < n; i += 128) {
+          const uint2 k = *reinterpret_cast<const uint2*>(keys + i);
+          if (k.y < bd) { bd = k.y; bi = k.x; }
+        }
+        const unsigned md = __reduce_min_sync(0xffffffffu, bd);
+        const unsigned mi = __reduce_min_sync(0xffffffffu, bd == md ? bi : 0xFFFFFFFFu);
+        if (md != 0xFFFFFFFFu && bd == md && bi == mi) keys[mi] = ~0ull;
+        if (lane == 0) cand[m] = md == 0xFFFFFFFFu ? ~0ull : (((unsigned long long)md << 32) | mi);
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const float* ns = prm.nom_s + (size_t)b * 3 * T1;
+      const float th = ns[2 * T1 + t];
+      const float cs = cosf(th), sn = sinf(th);
+      const float* px = prm.points + (size_t)b * 2 * N;
+      const float* py = px + N;
+      const float* vx = prm.velocities ? prm.velocities + (size_t)b * 2 * N : nullptr;
+      const float* vy = vx ? vx + N : nullptr;
+      const int total = 4 * cnt;
+      for (int m = 0; m < cnt; ++m) {
+        unsigned bd = 0xFFFFFFFFu, bi = 0xFFFFFFFFu;
+        int bpos = -1;
+        for (int c = lane; c < total; c += 32) {
+          const int w = c / cnt, r = c - w * cnt;
+          const uint2 k = *reinterpret_cast<const uint2*>(cands + w * M + r);
+          if (k.y < bd || (k.y == bd && k.x < bi)) { bd = k.y; bi = k.x; bpos = w * M + r; }
+        }
+        const unsigned md = __reduce_min_sync(0xffffffffu, bd);
+        const unsigned mi = __reduce_min_sync(0xffffffffu, bd == md ? bi : 0xFFFFFFFFu);
+        if (bpos >= 0 && bd == md && bi == mi) cands[bpos] = ~0ull;
+        if (lane == m) mine = ((unsigned long long)md << 32) | mi;
+        __syncwarp();
+      }
+      if (lane < cnt) {
+        unsigned idx = (unsigned)(mine & 0xffffffffull);
+        if (idx >= (unsigned)n) idx = 0;
+        uint32_t u = (uint32_t)(mine >> 32);
+        u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+        const float d = __uint_as_float(u);
+        float gx = px[idx], gy = py[idx];
+        if (vx) {
+          gx = flow(gx, vx[idx], prm.dt, t);
+          gy = flow(gy, vy[idx], prm.dt, t);
+        }
+        const size_t o = ((size_t)b * T1 + t) * M + lane;
+        float lx = 0.f, ly = 0.f;
+        for (int e = 0; e < E; ++e) {
+          const float m_e = smu[idx * E + e];
+          lx = fmaf(fmaf(sn, prm.geo.G[e][1], -cs * prm.geo.G[e][0]), m_e, lx);
+          ly = fmaf(fmaf(-cs, prm.geo.G[e][1], -sn * prm.geo.G[e][0]), m_e, ly);
+          prm.sel_mu[o * E + e] = m_e;
+        }
+        prm.sel_lam[o * 2 + 0] = lx; prm.sel_lam[o * 2 + 1] = ly;
+        prm.sel_pts[o * 2 + 0] = gx; prm.sel_pts[o * 2 + 1] = gy;
+        prm.sel_dist[o] = d;
+        if (t == 0 && lane == 0 && prm.min_dist) prm.min_dist[b] = d;
+      }
+    }
+    __syncthreads();
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tbase) : "memory");
 }
 
 }  // namespace nb
