@@ -267,22 +267,25 @@ def run_ours(args):
         pk = peaks()
         ach = flops / (dune_ms * 1e-3) / 1e12
         alg_bytes = 4.0 * B * ((2 * N) * (2 if cfg.dynamic else 1) + 3 * (T + 1)) + 4.0 * B * (T + 1) * cfg.M * 9
-        # executed tensor work: 3 HMMA passes (fp16 hi/lo split) over 4 hidden layers + the 8-wide head, per 16-row tile,
-        # plus one extra tile per (env, step) for the selected points
-        tiles = B * (T + 1) * ((N + 31) // 32 * 2 + 1)
-        hmma_flops = tiles * (4 * 24 + 6) * 2.0 * 16 * 8 * 16
+        # executed tensor work (3 passes of the fp16 hi/lo split): per 128-point tile 4 layers x 6 UMMA (128x32x16) + head 6 UMMA (128x16x16)
+        if args.dune_kernel == 2:
+            tiles = B * (T + 1) * ((N + 127) // 128)
+            exec_flops = tiles * (4 * 6 * 2.0 * 128 * 32 * 16 + 6 * 2.0 * 128 * 16 * 16)
+            kname = "dune_tc_kernel (tcgen05.mma kind::f16, A from TMEM, fp16 hi/lo split, 3 passes; SASS UTCHMMA / LDTM / STTM)"
+        else:
+            tiles = B * (T + 1) * ((N + 31) // 32 * 2 + 1)
+            exec_flops = tiles * (4 * 24 + 6) * 2.0 * 16 * 8 * 16
+            kname = "dune_mma_kernel (mma.sync m16n8k16 f16, hi/lo split, 3 passes; SASS HMMA.16816.F32)" if args.dune_kernel == 1 else "dune_kernel (all-FP32 FFMA reference variant)"
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "dune_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.workload)
         roof = dict(bound="tensor", achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"], traffic=traffic,
-                    kernel="dune_mma_kernel (mma.sync m16n8k16 f16, hi/lo split, 3 passes; SASS HMMA.16816.F32)", kernel_ms=dune_ms,
-                    share_of_step=K * dune_ms / ms, peak_source=pk["which"],
-                    algorithmic_flops_per_launch=flops,
-                    hmma_executed_tflops=hmma_flops / (dune_ms * 1e-3) / 1e12, hmma_legacy_peak_tflops_measured=555.0,
-                    frac_of_hmma_peak=hmma_flops / (dune_ms * 1e-3) / 1e12 / 555.0,
+                    kernel=kname, kernel_ms=dune_ms, share_of_step=K * dune_ms / ms, peak_source=pk["which"],
+                    algorithmic_flops_per_launch=flops, tensor_executed_tflops=exec_flops / (dune_ms * 1e-3) / 1e12,
                     algorithmic_bytes_per_launch=alg_bytes, hbm_gbs_if_bytes_only=alg_bytes / (dune_ms * 1e-3) / 1e9, hbm_peak_gbs=pk["hbm_gbs"],
-                    note="compute-bound path (SURVEY 8d): HBM < 1% utilised; limiter is instruction issue + MUFU (tanh), see DESIGN.md 3.1")
+                    note="compute-bound path (SURVEY 8d): HBM < 1% utilised; the GEMMs are 32-wide slices between per-point LayerNorm/tanh, "
+                         "so the kernel is bound by instruction issue and the MUFU pipe (2 MUFU per tanh), not by the tensor pipe -- DESIGN.md 3.1")
 
     # ---- cpu baseline (rank 0, N = 1 only), bounded sample ------------------------------------------
     cpu = None
@@ -298,7 +301,7 @@ def run_ours(args):
     if rank == 0:
         value = world * B / (ms * 1e-3)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
-                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 via fp16 hi/lo tensor-core split (ObsPointNet) / f64 (NRMP interior point)",
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32-accurate fp16 hi/lo split on tcgen05 tensor cores (ObsPointNet) / f64 (NRMP interior point)",
                     data="synthetic",
                     config=dict(workload=f"{args.workload} {cfg.name}: B={B}/GPU T={T} N={N} K={K} M={cfg.M} dyn={cfg.dynamic}", global_batch=world * B,
                                 parallelism=f"env-sharded x{world}, one all_gather of {per_env} floats/env per step",
