@@ -380,11 +380,14 @@ __global__ void __launch_bounds__(128, 5) dune_tc_kernel(const DuneParams prm, c
         }
         const size_t o = ((size_t)b * T1 + t) * M + lane;
         float lx = 0.f, ly = 0.f;
-        for (int e = 0; e < E; ++e) {  // lam = ((-R) G^T) mu   (dune.py:89)
-          const float m_e = smu[idx * E + e];
-          lx = fmaf(fmaf(sn, prm.geo.G[e][1], -cs * prm.geo.G[e][0]), m_e, lx);
-          ly = fmaf(fmaf(-cs, prm.geo.G[e][1], -sn * prm.geo.G[e][0]), m_e, ly);
-          prm.sel_mu[o * E + e] = m_e;
+#pragma unroll
+        for (int e = 0; e < kMaxEdges; ++e) {  // lam = ((-R) G^T) mu   (dune.py:89); constant indices keep geo in the constant bank
+          if (e < E) {
+            const float m_e = smu[idx * E + e];
+            lx = fmaf(fmaf(sn, prm.geo.G[e][1], -cs * prm.geo.G[e][0]), m_e, lx);
+            ly = fmaf(fmaf(-cs, prm.geo.G[e][1], -sn * prm.geo.G[e][0]), m_e, ly);
+            prm.sel_mu[o * E + e] = m_e;
+          }
         }
         prm.sel_lam[o * 2 + 0] = lx; prm.sel_lam[o * 2 + 1] = ly;
         prm.sel_pts[o * 2 + 0] = gx; prm.sel_pts[o * 2 + 1] = gy;
@@ -642,11 +645,14 @@ __global__ void __launch_bounds__(160, 4) dune_tc2_kernel(const DuneParams prm, 
         }
         const size_t o = ((size_t)b * T1 + t) * M + lane;
         float lx = 0.f, ly = 0.f;
-        for (int e = 0; e < E; ++e) {
-          const float m_e = smu[idx * E + e];
-          lx = fmaf(fmaf(sn, prm.geo.G[e][1], -cs * prm.geo.G[e][0]), m_e, lx);
-          ly = fmaf(fmaf(-cs, prm.geo.G[e][1], -sn * prm.geo.G[e][0]), m_e, ly);
-          prm.sel_mu[o * E + e] = m_e;
+#pragma unroll
+        for (int e = 0; e < kMaxEdges; ++e) {
+          if (e < E) {
+            const float m_e = smu[idx * E + e];
+            lx = fmaf(fmaf(sn, prm.geo.G[e][1], -cs * prm.geo.G[e][0]), m_e, lx);
+            ly = fmaf(fmaf(-cs, prm.geo.G[e][1], -sn * prm.geo.G[e][0]), m_e, ly);
+            prm.sel_mu[o * E + e] = m_e;
+          }
         }
         prm.sel_lam[o * 2 + 0] = lx; prm.sel_lam[o * 2 + 1] = ly;
         prm.sel_pts[o * 2 + 0] = gx; prm.sel_pts[o * 2 + 1] = gy;
