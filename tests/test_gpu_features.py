@@ -160,3 +160,42 @@ def test_pentagon_robot_five_edges_random_weights(dune_kernel, tmp_path):
     mk = lambda: op.OraclePAN(spec, w, T=10, iter_num=1, dune_max_num=N, nrmp_max_num=10, iter_threshold=0.0, adjust=onr.Adjust(**cfg.adjust))
     assert (_cmp(got, op.run_batch(mk, inp)) < TOL).all()
     assert pan.read_selection()["mu"].shape == (B, 11, 10, 5)
+
+
+@pytest.mark.parametrize("T,M", [(12, 8), (20, 12), (6, 3), (10, 1)])
+def test_generic_horizon_and_hinge_counts(T, M):
+    """Kernel paths that the five BASELINE configs do not reach: NRMP without compile-time (T, M) (generic offsets),
+    2T > 32 (two rows of the reduced system per lane), 8 hinge rows per lane, M = 1."""
+    import dataclasses
+
+    cfg = dataclasses.replace(CONFIGS["C4"], T=T, M=M, N=96, K=1)
+    B = 4
+    inp = make_inputs(cfg, B=B, scene="obstacles")
+    pan = make_pan(cfg, K=1, max_envs=B)
+    got = run_pan(pan, inp)
+    ref = op.run_batch(oracle_factory(cfg, K=1), inp)
+    err = _cmp(got, ref)
+    assert (err < TOL).all(), (T, M, err)
+    assert (pan.status.cpu().numpy() == 0).all()
+
+
+def test_pingpong_tcgen05_variant_in_subprocess():
+    """dune_tc2_kernel (two tiles in flight per CTA, issuer warp) is selected by NB_DUNE_TC=2 at process start."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, os; sys.path.insert(0, os.getcwd()); sys.path.insert(0, 'tests')\n"
+        "import numpy as np\n"
+        "from gpu_helpers import make_pan, run_pan\n"
+        "from helpers import CONFIGS, make_inputs\n"
+        "cfg = CONFIGS['C3']; inp = make_inputs(cfg, B=3)\n"
+        "a = make_pan(cfg, K=1, max_envs=3, dune_kernel=2); run_pan(a, inp); sa = a.read_selection()\n"
+        "b = make_pan(cfg, K=1, max_envs=3, dune_kernel=1); run_pan(b, inp); sb = b.read_selection()\n"
+        "assert np.allclose(sa['distance'].cpu().numpy(), sb['distance'].cpu().numpy(), atol=2e-5)\n"
+        "assert np.allclose(sa['points'].cpu().numpy(), sb['points'].cpu().numpy(), atol=1e-6)\n"
+        "print('pingpong ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, NB_DUNE_TC="2"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "pingpong ok" in r.stdout, r.stdout + r.stderr
