@@ -271,7 +271,7 @@ def run_ours(args):
         if args.dune_kernel == 2:
             tiles = B * (T + 1) * ((N + 127) // 128)
             exec_flops = tiles * (4 * 6 * 2.0 * 128 * 32 * 16 + 6 * 2.0 * 128 * 16 * 16)
-            kname = "dune_tc_kernel (tcgen05.mma kind::f16, A from TMEM, fp16 hi/lo split, 3 passes; SASS UTCHMMA / LDTM / STTM)"
+            kname = "dune_tcp_kernel (tcgen05.mma kind::f16, A from TMEM, fp16 hi/lo split, 3 passes + bias product; two tiles in flight per CTA; FFMA2/FHFMA epilogues; SASS UTCHMMA / LDTM / STTM)"
         else:
             tiles = B * (T + 1) * ((N + 31) // 32 * 2 + 1)
             exec_flops = tiles * (4 * 24 + 6) * 2.0 * 16 * 8 * 16

@@ -24,39 +24,71 @@ void build_tc_image(const float* w, int E, std::vector<unsigned char>& out) {
   // element (n, k) of a K-major operand with `lbo` bytes between the two 8-half K groups and `kstep` bytes per 16 of K
   auto at = [](int n, int k, int lbo, int kstep) { return (size_t)(k / 16) * kstep + ((k % 16) / 8) * lbo + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2; };
   float* fl = reinterpret_cast<float*>(out.data() + I::kFloatOff);
-  const int hidden_w[4] = {L::W3, L::W5, L::W8, L::W10}, hidden_b[4] = {L::B3, L::B5, L::B8, L::B10};
-  // layers fed by a tanh (MLP.3, MLP.8 and the head MLP.13) receive r = 1/(exp(2y)+1) instead of tanh(y) = 1 - 2r:
+  // the five dense layers: MLP.3, .5, .8, .10 and the head MLP.13 (E rows, zero padded to N = 32).
+  // Layers fed by a tanh (MLP.3, MLP.8, MLP.13) receive r = 1/(exp(2y)+1) instead of tanh(y) = 1 - 2r:
   //   W tanh + b = (b + rowsum(W)) + (-2 W) r
-  const bool after_tanh[4] = {true, false, true, false};
-  for (int l = 0; l < 4; ++l) {
-    const size_t base = (size_t)l * I::kHiddenStride;
-    for (int n = 0; n < 32; ++n) {
+  const int dense_w[5] = {L::W3, L::W5, L::W8, L::W10, L::W13}, dense_b[5] = {L::B3, L::B5, L::B8, L::B10, L::b13(E)};
+  const int rows[5] = {32, 32, 32, 32, E};
+  const bool after_tanh[5] = {true, false, true, false, true};
+  // Layers that feed a LayerNorm (MLP.0 -> LN1, MLP.5 -> LN6, MLP.10 -> LN11) are CENTRED here: LN subtracts the mean over
+  // the 32 outputs, which is linear, so W - colmean(W) and b - mean(b) deliver mean-free pre-activations for free.
+  const bool before_ln[5] = {false, true, false, true, false};
+  for (int l = 0; l < 5; ++l) {
+    const size_t base = (size_t)l * I::kLayerStride;
+    std::vector<double> W(32 * 32, 0.0), bv(32, 0.0);
+    for (int n = 0; n < rows[l]; ++n) {
       double rowsum = 0.0;
       for (int k = 0; k < 32; ++k) {
-        const float wv = w[hidden_w[l] + n * 32 + k];
-        rowsum += (double)wv;
+        const double wv = (double)w[dense_w[l] + n * 32 + k];
+        rowsum += wv;
+        W[n * 32 + k] = after_tanh[l] ? -2.0 * wv : wv;
+      }
+      bv[n] = (double)w[dense_b[l] + n] + (after_tanh[l] ? rowsum : 0.0);
+    }
+    if (before_ln[l]) {
+      for (int k = 0; k < 32; ++k) {
+        double m = 0.0;
+        for (int n = 0; n < 32; ++n) m += W[n * 32 + k];
+        for (int n = 0; n < 32; ++n) W[n * 32 + k] -= m / 32;
+      }
+      double m = 0.0;
+      for (int n = 0; n < 32; ++n) m += bv[n];
+      for (int n = 0; n < 32; ++n) bv[n] -= m / 32;
+    }
+    for (int n = 0; n < 32; ++n) {
+      for (int k = 0; k < 32; ++k) {
         uint16_t hi, lo;
-        split_half_tc(after_tanh[l] ? -2.0f * wv : wv, hi, lo);
+        split_half_tc((float)W[n * 32 + k], hi, lo);
         put(base + at(n, k, 512, 1024), hi);
         put(base + 2048 + at(n, k, 512, 1024), lo);
       }
-      fl[I::BH + 32 * l + n] = (float)((double)w[hidden_b[l] + n] + (after_tanh[l] ? rowsum : 0.0));
+      fl[I::BH + 32 * l + n] = (float)bv[n];
     }
   }
-  for (int n = 0; n < E; ++n) {  // head (after a tanh), N padded to 16 with zero rows
-    double rowsum = 0.0;
-    for (int k = 0; k < 32; ++k) {
-      const float wv = w[L::W13 + n * 32 + k];
-      rowsum += (double)wv;
-      uint16_t hi, lo;
-      split_half_tc(-2.0f * wv, hi, lo);
-      put(I::kHeadOff + at(n, k, 256, 512), hi);
-      put(I::kHeadOff + 1024 + at(n, k, 256, 512), lo);
+  for (int m = 0; m < 128; ++m)  // ONES(m, 0..2) = 1.0h, K-major with 2048 B between the two 8-wide K groups
+    for (int k = 0; k < 3; ++k) put(I::kOnesOff + (size_t)(m / 8) * 128 + (m % 8) * 16 + k * 2, 0x3C00);
+  for (int l = 0; l < 5; ++l)    // BIASB[l](n, 0..2) = three fp16 pieces of the (folded) bias
+    for (int n = 0; n < 32; ++n) {
+      float rest = fl[I::BH + 32 * l + n];
+      for (int k = 0; k < 3; ++k) {
+        const __half h = __float2half_rn(rest);
+        rest -= __half2float(h);
+        uint16_t bits;
+        memcpy(&bits, &h, 2);
+        put(I::kBiasBOff + (size_t)l * 1024 + at(n, k, 512, 1024), bits);
+      }
     }
-    fl[I::BHEAD + n] = (float)((double)w[L::b13(E) + n] + rowsum);
+  {  // layer 0 (2 -> 32), centred for LN1; both layouts (row-major for the first kernel, columns for the packed one)
+    double mx = 0.0, my = 0.0, mb = 0.0;
+    for (int j = 0; j < 32; ++j) { mx += w[L::W0 + 2 * j]; my += w[L::W0 + 2 * j + 1]; mb += w[L::B0 + j]; }
+    for (int j = 0; j < 32; ++j) {
+      fl[I::W0X + j] = (float)((double)w[L::W0 + 2 * j] - mx / 32);
+      fl[I::W0Y + j] = (float)((double)w[L::W0 + 2 * j + 1] - my / 32);
+      fl[I::W0 + 2 * j] = fl[I::W0X + j];
+      fl[I::W0 + 2 * j + 1] = fl[I::W0Y + j];
+      fl[I::B0 + j] = (float)((double)w[L::B0 + j] - mb / 32);
+    }
   }
-  memcpy(fl + I::W0, w + L::W0, 64 * 4);
-  memcpy(fl + I::B0, w + L::B0, 32 * 4);
   const int g_src[3] = {L::G1, L::G6, L::G11}, b_src[3] = {L::BE1, L::BE6, L::BE11};
   const int g_dst[3] = {I::G1, I::G6, I::G11}, b_dst[3] = {I::BE1, I::BE6, I::BE11};
   for (int q = 0; q < 3; ++q)
@@ -73,35 +105,34 @@ int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int sm_c
     return -3;
   }
   const int items = prm.B * (prm.T + 1);
-  static int force = -1;  // NB_DUNE_TC: developer switch, 1 = single-slot kernel, 2 = ping-pong kernel
+  static int force = -1;  // NB_DUNE_TC: developer switch, 1 = first (single-slot, scalar math) kernel, 2 = mbarrier hand-off
   if (force < 0) {
     const char* v = getenv("NB_DUNE_TC");
     force = v ? atoi(v) : 0;
   }
-  // The single-slot kernel with 5 CTAs per SM is the default: measured 2.49 ms per launch at C4 against 3.14 ms for the
-  // ping-pong kernel (two tiles in flight per CTA + issuer warp; its polling issuer and 4-CTA limit cost more than the
-  // intra-CTA overlap gains).  NB_DUNE_TC=2 selects the ping-pong kernel for experiments.
-  const bool pingpong = force == 2;
+  const bool single = force == 1;
+  const bool barrier_sync = force != 2;  // default: block barrier between operand stores and MMAs (2.19 ms vs 2.29 ms with the mbarrier hand-off)
   // TMEM columns are held by a CTA for its whole (persistent) lifetime: 512 / columns-per-CTA CTAs may share an SM, one
   // more would sit in tcgen05.alloc until another CTA exits, and the block scheduler knows nothing about TMEM
   // (observed: a 5th CTA with 128 columns landing on an SM turned 2.7 ms into 4.3 ms per launch).  The shared-memory
   // request is therefore padded so that never more CTAs fit than registers and TMEM admit.
-  const int threads = pingpong ? 160 : 128;
-  const int want = pingpong ? 4 : 5;  // ping-pong: 128 columns -> 4 CTAs;  single slot: 64 columns, 96 registers -> 5 CTAs
+  const int want = single ? 5 : 4;  // two-slot kernel: 128 columns -> 4 CTAs;  single slot: 64 columns, 96 registers -> 5 CTAs
   // smallest request that keeps a (want+1)-th CTA out (anything larger only shrinks the L1 cache: 44 KB instead of 38 KB
-  // per CTA cost 2.49 -> 3.50 ms per launch)
+  // per CTA cost 2.49 -> 3.50 ms per launch of the single-slot kernel)
   const size_t pad = (size_t)(233472 / (want + 1)) - 2048 + 512;
   if (smem < pad) smem = pad;
-  cudaError_t e = pingpong ? cudaFuncSetAttribute(dune_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(dune_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = single ? cudaFuncSetAttribute(dune_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : (barrier_sync ? cudaFuncSetAttribute(dune_tcp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                         : cudaFuncSetAttribute(dune_tcp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (e == cudaSuccess) {
     int per_sm = (int)(233472 / (smem + 2048));
     if (per_sm > want) per_sm = want;
     if (per_sm < 1) per_sm = 1;
     int grid = sm_count * per_sm;
     if (grid > items) grid = items;
-    if (pingpong) dune_tc2_kernel<<<grid, threads, smem, st>>>(prm, d_image);
-    else dune_tc_kernel<<<grid, threads, smem, st>>>(prm, d_image);
+    if (single) dune_tc_kernel<<<grid, 128, smem, st>>>(prm, d_image);
+    else if (barrier_sync) dune_tcp_kernel<0><<<grid, 128, smem, st>>>(prm, d_image);
+    else dune_tcp_kernel<1><<<grid, 128, smem, st>>>(prm, d_image);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {

@@ -72,6 +72,44 @@ __global__ void k_mufu(float* out) {
   float s = 0; for (int i = 0; i < ILP; ++i) s += c[i];
   if (s == 123.f) out[0] = s;
 }
+// packed fp32 (Blackwell FFMA2): one issue slot, two FMAs
+__global__ void k_ffma2(float* out) {
+  unsigned long long c[ILP], a, b;
+  float a0 = threadIdx.x * 1e-9f, b0 = 0.999f;
+  asm("mov.b64 %0, {%1,%1};" : "=l"(a) : "f"(a0));
+  asm("mov.b64 %0, {%1,%1};" : "=l"(b) : "f"(b0));
+  for (int i = 0; i < ILP; ++i) { float f = i; asm("mov.b64 %0, {%1,%1};" : "=l"(c[i]) : "f"(f)); }
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(c[i]) : "l"(b), "l"(a));
+  }
+  unsigned long long s = 0; for (int i = 0; i < ILP; ++i) s ^= c[i];
+  if (s == 123ull) out[0] = 1.f;
+}
+// issue-slot experiment: per MUFU, 4 scalar FFMA (PACK=0) or 2 FFMA2 (PACK=1) doing the same arithmetic
+template <int PACK>
+__global__ void k_mix(float* out) {
+  float m[ILP]; unsigned long long c[ILP][2], a, b;
+  float a0 = threadIdx.x * 1e-9f, b0 = 0.999f;
+  asm("mov.b64 %0, {%1,%1};" : "=l"(a) : "f"(a0));
+  asm("mov.b64 %0, {%1,%1};" : "=l"(b) : "f"(b0));
+  for (int i = 0; i < ILP; ++i) { float f = i; m[i] = 0.5f + f * 0.01f; asm("mov.b64 %0, {%1,%1};" : "=l"(c[i][0]) : "f"(f)); c[i][1] = c[i][0]; }
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(m[i]));
+      if (PACK) {
+        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(c[i][0]) : "l"(b), "l"(a));
+        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(c[i][1]) : "l"(b), "l"(a));
+      } else {
+        asm volatile("{.reg .f32 x,y,p,q,r,s; mov.b64 {x,y}, %0; mov.b64 {p,q}, %1; mov.b64 {r,s}, %2; fma.rn.f32 x,x,p,r; fma.rn.f32 y,y,q,s; mov.b64 %0, {x,y};}" : "+l"(c[i][0]) : "l"(b), "l"(a));
+        asm volatile("{.reg .f32 x,y,p,q,r,s; mov.b64 {x,y}, %0; mov.b64 {p,q}, %1; mov.b64 {r,s}, %2; fma.rn.f32 x,x,p,r; fma.rn.f32 y,y,q,s; mov.b64 %0, {x,y};}" : "+l"(c[i][1]) : "l"(b), "l"(a));
+      }
+    }
+  }
+  unsigned long long s = 0; float t = 0; for (int i = 0; i < ILP; ++i) { s ^= c[i][0] ^ c[i][1]; t += m[i]; }
+  if (s == 123ull || t == 123.f) out[0] = 1.f;
+}
 __global__ void k_dfma(double* out) {
   double c[ILP]; double a = threadIdx.x * 1e-9, b = 0.999;
   for (int i = 0; i < ILP; ++i) c[i] = i;
@@ -107,6 +145,9 @@ int main() {
     rep("mma f16", timeit([&] { k_mma_f16<<<blocks, th>>>(d); }), 16 * 8 * 16, "MAC");
     rep("mma bf16", timeit([&] { k_mma_bf16<<<blocks, th>>>(d); }), 16 * 8 * 16, "MAC");
     rep("ffma", timeit([&] { k_ffma<<<blocks, th>>>(d); }), 32, "FMA");
+    rep("ffma2 (x2)", timeit([&] { k_ffma2<<<blocks, th>>>(d); }), 64, "FMA");
+    rep("mix 4ffma+ex2", timeit([&] { k_mix<0><<<blocks, th>>>(d); }), 32, "grp");
+    rep("mix 2ffma2+ex2", timeit([&] { k_mix<1><<<blocks, th>>>(d); }), 32, "grp");
     rep("dfma", timeit([&] { k_dfma<<<blocks, th>>>(dd); }), 32, "FMA");
     rep("ex2", timeit([&] { k_mufu<0><<<blocks, th>>>(d); }), 32, "op");
     rep("rcp", timeit([&] { k_mufu<1><<<blocks, th>>>(d); }), 32, "op");
