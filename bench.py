@@ -270,7 +270,7 @@ def run_ours(args):
         # executed tensor work (3 passes of the fp16 hi/lo split): per 128-point tile 4 layers x 6 UMMA (128x32x16) + head 6 UMMA (128x16x16)
         if args.dune_kernel == 2:
             tiles = B * (T + 1) * ((N + 127) // 128)
-            exec_flops = tiles * (4 * 6 * 2.0 * 128 * 32 * 16 + 6 * 2.0 * 128 * 16 * 16)
+            exec_flops = tiles * 5 * 7 * 2.0 * 128 * 32 * 16  # 5 dense layers x (bias product + 6 UMMA 128x32x16)
             kname = "dune_tcp_kernel (tcgen05.mma kind::f16, A from TMEM, fp16 hi/lo split, 3 passes + bias product; two tiles in flight per CTA; FFMA2/FHFMA epilogues; SASS UTCHMMA / LDTM / STTM)"
         else:
             tiles = B * (T + 1) * ((N + 31) // 32 * 2 + 1)

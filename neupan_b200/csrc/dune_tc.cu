@@ -1,4 +1,5 @@
 // Translation unit of the tcgen05 DUNE kernel: host-side operand image + launcher.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,7 +17,9 @@ static inline void split_half_tc(float v, uint16_t& hi, uint16_t& lo) {
 }
 
 // packed checkpoint (WeightLayout order, E outputs) -> TcImage bytes (canonical K-major / no-swizzle UMMA layout)
-void build_tc_image(const float* w, int E, std::vector<unsigned char>& out) {
+// returns flags: bit 0 = every tanh argument of the network is bounded by 30 in exp2 units (|LN(x)_j| <= sqrt(32)), which
+// allows the kernel's shared-reciprocal tanh (ln_tanh_split<true>)
+int build_tc_image(const float* w, int E, std::vector<unsigned char>& out) {
   using L = WeightLayout;
   using I = TcImage;
   out.assign(I::kBytes, 0);
@@ -96,9 +99,16 @@ void build_tc_image(const float* w, int E, std::vector<unsigned char>& out) {
       fl[g_dst[q] + i] = (float)((double)w[g_src[q] + i] * 2.8853900817779268);
       fl[b_dst[q] + i] = (float)((double)w[b_src[q] + i] * 2.8853900817779268);
     }
+  double amax = 0.0;
+  for (int q = 0; q < 3; ++q)
+    for (int i = 0; i < 32; ++i) {
+      const double a = std::fabs((double)fl[g_dst[q] + i]) * 5.6568542494923806 + std::fabs((double)fl[b_dst[q] + i]);  // sqrt(32)
+      if (!(a <= amax)) amax = a;  // NaN-propagating max
+    }
+  return amax <= 30.0 ? 1 : 0;
 }
 
-int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, cudaStream_t st, char* err, size_t errlen) {
+int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int image_flags, int sm_count, int max_smem_optin, cudaStream_t st, char* err, size_t errlen) {
   size_t smem = dune_tc_smem_bytes(prm.N, prm.geo.E, prm.M);
   if ((long long)smem > max_smem_optin) {
     snprintf(err, errlen, "N=%d needs %zu B of shared memory (limit %d)", prm.N, smem, max_smem_optin);
@@ -121,20 +131,22 @@ int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int sm_c
   // per CTA cost 2.49 -> 3.50 ms per launch of the single-slot kernel)
   const size_t pad = (size_t)(233472 / (want + 1)) - 2048 + 512;
   if (smem < pad) smem = pad;
-  cudaError_t e = single ? cudaFuncSetAttribute(dune_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                         : (barrier_sync ? cudaFuncSetAttribute(dune_tcp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                         : cudaFuncSetAttribute(dune_tcp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (e == cudaSuccess) {
+  const bool fast = (image_flags & 1) != 0 && force != 4;  // NB_DUNE_TC=4: plain reciprocals
+  auto run = [&](auto kern, int threads) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     int per_sm = (int)(233472 / (smem + 2048));
     if (per_sm > want) per_sm = want;
     if (per_sm < 1) per_sm = 1;
     int grid = sm_count * per_sm;
     if (grid > items) grid = items;
-    if (single) dune_tc_kernel<<<grid, 128, smem, st>>>(prm, d_image);
-    else if (barrier_sync) dune_tcp_kernel<0><<<grid, 128, smem, st>>>(prm, d_image);
-    else dune_tcp_kernel<1><<<grid, 128, smem, st>>>(prm, d_image);
-    e = cudaGetLastError();
-  }
+    kern<<<grid, threads, smem, st>>>(prm, d_image);
+    return cudaGetLastError();
+  };
+  cudaError_t e;
+  if (single) e = run(dune_tc_kernel, 128);
+  else if (barrier_sync) e = fast ? run(dune_tcp_kernel<0, true>, 128) : run(dune_tcp_kernel<0, false>, 128);
+  else e = fast ? run(dune_tcp_kernel<1, true>, 128) : run(dune_tcp_kernel<1, false>, 128);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "dune_tc kernel launch failed: %s", cudaGetErrorString(e));
     return -2;

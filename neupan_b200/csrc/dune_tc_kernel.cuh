@@ -216,6 +216,10 @@ __device__ __forceinline__ void ld32p(uint32_t taddr, f2 (&hp)[16]) {
 // LayerNorm (eps 1e-5, biased variance) + r = 1/(exp2(.)+1) + fp16 split, two features per instruction where the ISA
 // allows it (squares, scale/offset, +1); MUFU.EX2 / MUFU.RCP stay scalar.  The inputs arrive CENTRED: the layer that
 // produces them has W - colmean(W), b - mean(b) (host image), so mean(h) = 0 up to rounding and only the variance is left.
+// kFast: one MUFU.RCP serves four features: with d_i = exp2(a_i) + 1,  t = 1/(d0 d1 d2 d3),  1/d0 = t d1 d2 d3, ...  (three
+// packed and three scalar multiplies instead of three MUFUs; the host enables it only if the checkpoint's LayerNorm
+// gains/offsets bound every a_i by 30, so that the product of four stays below 2^124)
+template <bool kFast>
 __device__ __forceinline__ void ln_tanh_split(f2 (&hp)[16], const float* __restrict__ g, const float* __restrict__ be, uint32_t (&hi)[16],
                                               uint32_t (&lo)[16]) {
   f2 qa = 0ull, qb = 0ull, qc = 0ull, qd = 0ull;
@@ -235,20 +239,37 @@ __device__ __forceinline__ void ln_tanh_split(f2 (&hp)[16], const float* __restr
   for (int c = 0; c < 16; c += 2) {
     const ulonglong2 gg = *reinterpret_cast<const ulonglong2*>(g + 2 * c);
     const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(be + 2 * c);
-    const f2 ga[2] = {gg.x, gg.y}, ba[2] = {bb.x, bb.y};
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      float a0, a1, e0, e1, d0, d1, r0, r1;
-      upk(fma2(mul2(hp[c + u], r2), ga[u], ba[u]), a0, a1);
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
-      upk(add2(pk(e0, e1), one2), d0, d1);
+    float a0, a1, a2, a3, e0, e1, e2, e3;
+    upk(fma2(mul2(hp[c], r2), gg.x, bb.x), a0, a1);
+    upk(fma2(mul2(hp[c + 1], r2), gg.y, bb.y), a2, a3);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(a2));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(a3));
+    const f2 da = add2(pk(e0, e1), one2), db = add2(pk(e2, e3), one2);  // (d0, d1), (d2, d3)
+    float r0, r1, r2s, r3;
+    if (kFast) {
+      float p0, p1, t;
+      upk(mul2(da, db), p0, p1);  // (d0 d2, d1 d3)
+      const float pp = p0 * p1;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(pp));
+      const f2 u = pk(t * p1, t * p0);  // (1/(d0 d2), 1/(d1 d3))
+      upk(mul2(u, db), r0, r1);         // 1/d0, 1/d1
+      upk(mul2(u, da), r2s, r3);        // 1/d2, 1/d3
+    } else {
+      float d0, d1, d2, d3;
+      upk(da, d0, d1);
+      upk(db, d2, d3);
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
-      split_pair(r0, r1, hi[c + u], lo[c + u]);
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r2s) : "f"(d2));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r3) : "f"(d3));
     }
+    split_pair(r0, r1, hi[c], lo[c]);
+    split_pair(r2s, r3, hi[c + 1], lo[c + 1]);
   }
 }
+
 // relu + split without a max: hi = fp16x2(relu(a)) rounded TOWARDS ZERO (cvt.rz.relu), so that a - hi is >= 0 for a > 0
 // and equals a < 0 for a <= 0 (hi = 0); lo = fp16x2(relu(a - hi)) then drops exactly the negative inputs
 __device__ __forceinline__ void relu_split(const f2 (&hp)[16], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
@@ -488,7 +509,7 @@ __device__ __forceinline__ void select_and_write_reg(const DuneParams& prm, cons
 //   Element-wise math is packed two features per instruction (FFMA2/FADD2/FMUL2) and the fp16 split uses FHFMA.
 // kSync = 0: a block barrier between the operand stores of a slot and its MMAs;  kSync = 1: the four warps arrive on an
 // mbarrier instead and only warp 0 (whose lane 0 issues the MMAs) waits for it, so warps 1-3 run ahead into the other slot.
-template <int kSync>
+template <int kSync, bool kFast>
 __global__ void __launch_bounds__(128, 4) dune_tcp_kernel(const DuneParams prm, const unsigned char* __restrict__ image) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];  // the attribute aligns the dynamic segment (UMMA operands need 128 B)
   using I = TcImage;
@@ -587,7 +608,7 @@ __global__ void __launch_bounds__(128, 4) dune_tcp_kernel(const DuneParams prm, 
           hp[c + 1] = tc::fma2(wy.y, y2, tc::fma2(wx.y, x2, bb.y));
         }
         uint32_t hi[16], lo[16];
-        tc::ln_tanh_split(hp, fl + I::G1, fl + I::BE1, hi, lo);
+        tc::ln_tanh_split<kFast>(hp, fl + I::G1, fl + I::BE1, hi, lo);
         publish(hi, lo, sl, 0);
       }
 #pragma unroll 1
@@ -599,7 +620,7 @@ __global__ void __launch_bounds__(128, 4) dune_tcp_kernel(const DuneParams prm, 
           acquire(sl);
           tc::ld32p(trow + 64 * sl, hp);
           if (st & 1) tc::relu_split(hp, hi, lo);
-          else tc::ln_tanh_split(hp, fl + I::G1 + 32 * st, fl + I::BE1 + 32 * st, hi, lo);  // st = 2: G6/BE6, st = 4: G11/BE11
+          else tc::ln_tanh_split<kFast>(hp, fl + I::G1 + 32 * st, fl + I::BE1 + 32 * st, hi, lo);  // st = 2: G6/BE6, st = 4: G11/BE11
           publish(hi, lo, sl, st);
         }
       }

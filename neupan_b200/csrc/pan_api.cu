@@ -20,8 +20,8 @@ void build_mma_image(const float* w, int E, std::vector<unsigned char>& out);
 int launch_dune_mma(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, int cta_per_sm_limit, cudaStream_t st,
                     char* err, size_t errlen);
 // dune_tc.cu
-void build_tc_image(const float* w, int E, std::vector<unsigned char>& out);
-int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, cudaStream_t st, char* err, size_t errlen);
+int build_tc_image(const float* w, int E, std::vector<unsigned char>& out);
+int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int image_flags, int sm_count, int max_smem_optin, cudaStream_t st, char* err, size_t errlen);
 }  // namespace nb
 
 namespace {
@@ -59,6 +59,7 @@ struct nb_pan {
   float* d_weights = nullptr;
   unsigned char* d_image = nullptr;  // fragment-ordered fp16 hi/lo weight image of the mma.sync DUNE kernel
   unsigned char* d_tc_image = nullptr;  // UMMA operand image of the tcgen05 DUNE kernel
+  int tc_flags = 0;                     // build_tc_image(): bit 0 = bounded tanh arguments
   int dune_variant = 2;              // NB_OPT_DUNE_KERNEL: 0 = FP32 FFMA, 1 = mma.sync tensor-core, 2 = tcgen05 tensor-core kernel
   int overlap = 1;                   // NB_OPT_OVERLAP: number of env sub-batches pipelined on internal streams
   cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -96,7 +97,7 @@ int launch_dune(nb_pan* p, const nb::DuneParams& prm, cudaStream_t st, int cta_l
   int rc = NB_ERR_INVALID;
   char msg[256] = "";
   if (p->dune_variant == 2) {
-    rc = nb::launch_dune_tc(prm, p->d_tc_image, p->sm_count, p->max_smem_optin, st, msg, sizeof(msg));
+    rc = nb::launch_dune_tc(prm, p->d_tc_image, p->tc_flags, p->sm_count, p->max_smem_optin, st, msg, sizeof(msg));
     if (rc) return fail(rc, "%s", msg);
     ++g_launches;
     return NB_OK;
@@ -253,7 +254,7 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
     nb::build_mma_image(weights, cfg->edge_dim, image);
     NB_CUDA(dalloc(&p->d_image, image.size()));
     NB_CUDA(cudaMemcpy(p->d_image, image.data(), image.size(), cudaMemcpyHostToDevice));
-    nb::build_tc_image(weights, cfg->edge_dim, image);
+    p->tc_flags = nb::build_tc_image(weights, cfg->edge_dim, image);
     NB_CUDA(dalloc(&p->d_tc_image, image.size()));
     NB_CUDA(cudaMemcpy(p->d_tc_image, image.data(), image.size(), cudaMemcpyHostToDevice));
   }

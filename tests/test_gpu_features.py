@@ -179,8 +179,11 @@ def test_generic_horizon_and_hinge_counts(T, M):
     assert (pan.status.cpu().numpy() == 0).all()
 
 
-def test_single_slot_tcgen05_variant_in_subprocess():
-    """The first tcgen05 kernel (one tile per CTA, scalar math) is selected by NB_DUNE_TC=1 at process start."""
+@pytest.mark.parametrize("variant", ["1", "2", "4"])
+def test_tcgen05_kernel_variants_in_subprocess(variant):
+    """NB_DUNE_TC (read at process start) selects the other tcgen05 kernels: 1 = first single-slot kernel with scalar
+    math, 2 = two-slot kernel with the mbarrier hand-off instead of the block barrier, 4 = plain reciprocals instead of
+    the shared-reciprocal tanh.  Each must agree with the mma.sync kernel."""
     import os
     import subprocess
     import sys
@@ -195,7 +198,7 @@ def test_single_slot_tcgen05_variant_in_subprocess():
         "b = make_pan(cfg, K=1, max_envs=3, dune_kernel=1); run_pan(b, inp); sb = b.read_selection()\n"
         "assert np.allclose(sa['distance'].cpu().numpy(), sb['distance'].cpu().numpy(), atol=2e-5)\n"
         "assert np.allclose(sa['points'].cpu().numpy(), sb['points'].cpu().numpy(), atol=1e-6)\n"
-        "print('single-slot ok')\n")
+        "print('variant ok')\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, NB_DUNE_TC="1"), capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "single-slot ok" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, NB_DUNE_TC=variant), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout + r.stderr
