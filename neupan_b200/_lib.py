@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libneupan_b200.so")
+# NEUPAN_B200_LIB: developer override (A/B runs of two builds of the same library)
+LIB_PATH = os.environ.get("NEUPAN_B200_LIB") or os.path.join(HERE, "lib", "libneupan_b200.so")
 
 NB_KIN = {"diff": 0, "acker": 1, "omni": 2}
 NB_OK, NB_ERR_INVALID, NB_ERR_CUDA, NB_ERR_CAPACITY, NB_ERR_NO_DEVICE = 0, -1, -2, -3, -4

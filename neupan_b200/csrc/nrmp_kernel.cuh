@@ -69,7 +69,7 @@ __host__ __device__ inline size_t nrmp_warp_doubles(int T, int M) {
   n += 3 * (size_t)T * (T + 1);    // F, packed: row t keeps only its 2(t+1) structurally non-zero columns at offset t(t+1)
   n += 3 * (size_t)T;              // s0
   n += (size_t)nU * (nU + 1) / 2;  // Hc
-  n += (size_t)nU * (nU + 1);      // H (padded rows)
+  n += (size_t)nU * (nU + 3) / 2;  // H / Cholesky factor: lower triangle, row i at i(i+3)/2 (one pad element per row)
   n += nrmp_scratch_doubles(T, M);
   n += 4 * (size_t)nU;             // cv, x, rdU, dU
   n += 14 * (size_t)T;             // per-step scalars
@@ -127,8 +127,11 @@ __device__ __forceinline__ float rcpf(double x) {
 // TT, MM: compile-time horizon / hinge rows per step (0 = read them from the parameters).  With constants every
 // workspace offset, loop bound and row stride folds into immediates -- half of the generic kernel's
 // instructions were integer address arithmetic.
+// Residency: the (10, 10) specialisation is built for 7 CTAs (14 warps) per SM -- 128 registers with ~200 B of spills and
+// 29 KB of shared memory per CTA.  At B = 4096 that is 2072 resident solves = two full rounds instead of 2.3 rounds of
+// 1776; measured 1.39 -> 1.25 ms per launch.  (__maxnreg__(144) instead of the min-blocks bound spills more and is slower.)
 template <int HPL, bool SMALL, int TT, int MM>
-__global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpParams prm, int warps_per_cta, int warp_doubles_rt) {
+__global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6 : 4)) nrmp_kernel(const NrmpParams prm, int warps_per_cta, int warp_doubles_rt) {
   extern __shared__ __align__(16) double smem_d[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int T = TT > 0 ? TT : prm.T, M = TT > 0 ? MM : prm.M, T1 = T + 1;
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
   const int nP = nU * (nU + 1) / 2;
   const int oBU = 0, oBL = nU, oRU = 2 * nU, oRL = oRU + nR, oDU = oRL + nR, oDL = oDU + TD;
   const int mb = oDL + TD;
-  const int HS = nU + 1;
+  auto hrow = [](int i) { return (i * (i + 3)) >> 1; };  // offset of row i of the lower-triangular H / L
 
   // pair table (i << 8 | j) of the lower triangle, shared by the CTA
   unsigned short* ptab = reinterpret_cast<unsigned short*>(smem_d + (size_t)warps_per_cta * warp_doubles);
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
   double* F = wsp;            wsp += 3 * FT;       // F[r][t][j] at r*FT + t(t+1) + j, j < 2(t+1)  (zero beyond)
   double* s0 = wsp;           wsp += 3 * T;        // s0[r][t]
   double* Hc = wsp;           wsp += nP;
-  double* H = wsp;            wsp += nU * HS;
+  double* H = wsp;            wsp += (nU * (nU + 3)) >> 1;
   double* scratch = wsp;      wsp += nrmp_scratch_doubles(T, M);
   double* Gx = scratch;  double* Gy = scratch + FT;  // Hessian assembly (same packing as F)
   double* tmpk = scratch;                                // per-hinge values published for the per-step sums
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
         } else if (i == j + 2) {
           acc -= cz[oRU + j] * (double)cis[oRU + j] + cz[oRL + j] * (double)cis[oRL + j];
         }
-        H[i * HS + j] = acc;
+        H[hrow(i) + j] = acc;
       }
       __syncwarp();
       // (d) Cholesky, left-looking by column; lane owns rows lane, lane+32; inverse diagonal in registers
@@ -489,15 +492,15 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
       for (int k = 0; k < nU; ++k) {
         double acc0 = 0.0, acc1 = 0.0;
         const int i0 = lane, i1 = lane + 32;
-        const double* rowk = H + k * HS;
+        const double* rowk = H + hrow(k);
         if (i0 >= k && i0 < nU) {
-          const double* rowi = H + i0 * HS;
+          const double* rowi = H + hrow(i0);
           acc0 = rowi[k];
 #pragma unroll 4
           for (int p = 0; p < k; ++p) acc0 -= rowi[p] * rowk[p];
         }
         if (!SMALL && i1 >= k && i1 < nU) {
-          const double* rowi = H + i1 * HS;
+          const double* rowi = H + hrow(i1);
           acc1 = rowi[k];
 #pragma unroll 4
           for (int p = 0; p < k; ++p) acc1 -= rowi[p] * rowk[p];
@@ -507,8 +510,8 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
         const double ild = rsqrt64(d);
         if (i0 == k) invd0 = ild;
         if (!SMALL && i1 == k) invd1 = ild;
-        if (i0 >= k && i0 < nU) H[i0 * HS + k] = acc0 * ild;
-        if (!SMALL && i1 >= k && i1 < nU) H[i1 * HS + k] = acc1 * ild;
+        if (i0 >= k && i0 < nU) H[hrow(i0) + k] = acc0 * ild;
+        if (!SMALL && i1 >= k && i1 < nU) H[hrow(i1) + k] = acc1 * ild;
         __syncwarp();
       }
       if (bad) { stat |= 2; break; }
@@ -569,7 +572,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
           }
         }
         if (SMALL) {
-          const double* rowl = H + lane * HS;  // L[lane][k], k < lane
+          const double* rowl = H + hrow(lane);  // L[lane][k], k < lane
 #pragma unroll 2
           for (int k = 0; k < nU; ++k) {
             const double yk = __shfl_sync(0xffffffffu, r0 * invd0, k);
@@ -581,7 +584,7 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
           for (int k = nU - 1; k >= 0; --k) {
             const double xk = __shfl_sync(0xffffffffu, r0 * invd0, k);
             if (lane == k) r0 = xk;
-            if (lane < k) r0 -= coll[k * HS] * xk;
+            if (lane < k) r0 -= coll[hrow(k)] * xk;
           }
         } else {
 #pragma unroll 1
@@ -589,16 +592,16 @@ __global__ void __launch_bounds__(64, HPL <= 4 ? 6 : 4) nrmp_kernel(const NrmpPa
             const double mine = k < 32 ? r0 * invd0 : r1 * invd1;
             const double yk = __shfl_sync(0xffffffffu, mine, k & 31);
             if (lane == (k & 31)) { if (k < 32) r0 = yk; else r1 = yk; }
-            if (lane > k && lane < nU) r0 -= H[lane * HS + k] * yk;
-            if (lane + 32 > k && lane + 32 < nU) r1 -= H[(lane + 32) * HS + k] * yk;
+            if (lane > k && lane < nU) r0 -= H[hrow(lane) + k] * yk;
+            if (lane + 32 > k && lane + 32 < nU) r1 -= H[hrow(lane + 32) + k] * yk;
           }
 #pragma unroll 1
           for (int k = nU - 1; k >= 0; --k) {
             const double mine = k < 32 ? r0 * invd0 : r1 * invd1;
             const double xk = __shfl_sync(0xffffffffu, mine, k & 31);
             if (lane == (k & 31)) { if (k < 32) r0 = xk; else r1 = xk; }
-            if (lane < k) r0 -= H[k * HS + lane] * xk;
-            if (lane + 32 < k) r1 -= H[k * HS + lane + 32] * xk;
+            if (lane < k) r0 -= H[hrow(k) + lane] * xk;
+            if (lane + 32 < k) r1 -= H[hrow(k) + lane + 32] * xk;
           }
         }
         if (lane < nU) dU[lane] = r0;
