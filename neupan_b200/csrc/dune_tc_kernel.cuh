@@ -433,15 +433,21 @@ __device__ __forceinline__ void issue_layer(uint32_t tD, uint32_t wsmem, uint32_
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// same, but D is initialised by the bias product ONES . BIASB[layer] instead of a tcgen05.st of the bias row
-__device__ __forceinline__ void issue_layer_bias(uint32_t tD, uint32_t img_smem, int layer, uint32_t bar) {
+// same, but D is initialised by the bias product ONES . BIASB[layer] instead of a tcgen05.st of the bias row.
+// The descriptors are linear in the operand address (all operands are 16-byte multiples inside one 1024-aligned image and
+// shared memory addresses fit the 14-bit field), so they are formed by adding constants to two precomputed low words:
+//   dw = descriptor low word of the image base with LBO 512 (weights, BIASB), done = same for ONES (LBO 2048)
+constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version bit 46
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
+__device__ __forceinline__ void issue_layer_bias(uint32_t tD, uint32_t dw, uint32_t done, int layer, uint32_t bar) {
   using I = TcImage;
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  mma_f16_ss(tD, b_desc(img_smem + I::kOnesOff, 2048), b_desc(img_smem + I::kBiasBOff + layer * 1024, 512), kIdescN32, 0u);
-  const uint32_t wsmem = img_smem + layer * I::kLayerStride;
+  mma_f16_ss(tD, mk_desc(done), mk_desc(dw + (I::kBiasBOff >> 4) + layer * (1024 >> 4)), kIdescN32, 0u);
+  const uint32_t w = dw + layer * (I::kLayerStride >> 4);
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    const uint64_t bhi = b_desc(wsmem + s * 1024, 512), blo = b_desc(wsmem + 2048 + s * 1024, 512);
+    const uint64_t bhi = mk_desc(w + s * (1024 >> 4)), blo = mk_desc(w + (2048 >> 4) + s * (1024 >> 4));
     mma_f16(tD, tD + 48 + 8 * s, bhi, kIdescN32, 1u);  // A_lo . B_hi
     mma_f16(tD, tD + 32 + 8 * s, blo, kIdescN32, 1u);  // A_hi . B_lo
     mma_f16(tD, tD + 32 + 8 * s, bhi, kIdescN32, 1u);  // A_hi . B_hi
@@ -548,6 +554,7 @@ __global__ void __launch_bounds__(128, 4) dune_tcp_kernel(const DuneParams prm, 
   const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
   const uint32_t simg_u = tc::smem_u32(simg);
   const uint32_t bar0 = tc::smem_u32(&mbar[0]);
+  const uint32_t desc_w = tc::desc_lo(simg_u, 512), desc_ones = tc::desc_lo(simg_u + I::kOnesOff, 2048);
   uint32_t phases = 0;  // bit sl: parity of the next completion of mbar[sl];  bit 2 + sl: same for mbar[2 + sl]
 
   // activations (already split) of `slot` -> TMEM, then one thread starts the layer's MMAs (bias product first)
@@ -576,7 +583,7 @@ __global__ void __launch_bounds__(128, 4) dune_tcp_kernel(const DuneParams prm, 
     if (warp == issuer) {  // warp-uniform branch; elect.sync picks the issuing lane (no divergent-branch waterfall around UTCHMMA)
       uint32_t elected;
       asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(elected));
-      if (elected) tc::issue_layer_bias(tbase + 64 * slot, simg_u, layer, bar0 + 8 * slot);
+      if (elected) tc::issue_layer_bias(tbase + 64 * slot, desc_w, desc_ones, layer, bar0 + 8 * slot);
     }
   };
   auto acquire = [&](int slot) {

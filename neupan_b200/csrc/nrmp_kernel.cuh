@@ -485,34 +485,71 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
         H[hrow(i) + j] = acc;
       }
       __syncwarp();
-      // (d) Cholesky, left-looking by column; lane owns rows lane, lane+32; inverse diagonal in registers
+      // (d) Cholesky, left-looking; lane owns rows lane, lane+32; inverse diagonal in registers.
+      //     SMALL: two columns per step (nU = 2T is even) -- row i is read once for both dot products, which are two
+      //     independent FMA chains; the second column then takes the rank-1 correction of the first.
       bool bad = false;
       double invd0 = 0.0, invd1 = 0.0;
+      if (SMALL) {
 #pragma unroll 1
-      for (int k = 0; k < nU; ++k) {
-        double acc0 = 0.0, acc1 = 0.0;
-        const int i0 = lane, i1 = lane + 32;
-        const double* rowk = H + hrow(k);
-        if (i0 >= k && i0 < nU) {
-          const double* rowi = H + hrow(i0);
-          acc0 = rowi[k];
+        for (int k = 0; k < nU; k += 2) {
+          const double* rowk = H + hrow(k);
+          const double* rowk1 = H + hrow(k + 1);
+          const bool in0 = lane >= k && lane < nU, in1 = lane > k && lane < nU;
+          double a0 = 0.0, a1 = 0.0;
+          if (in0) {
+            const double* rowi = H + hrow(lane);
+            a0 = rowi[k];
+            if (in1) a1 = rowi[k + 1];
 #pragma unroll 4
-          for (int p = 0; p < k; ++p) acc0 -= rowi[p] * rowk[p];
+            for (int p = 0; p < k; ++p) {
+              const double v = rowi[p];
+              a0 -= v * rowk[p];
+              a1 -= v * rowk1[p];
+            }
+          }
+          const double d0 = __shfl_sync(0xffffffffu, a0, k);
+          if (!(d0 > 0.0)) { bad = true; break; }
+          const double ild0 = rsqrt64(d0);
+          const double l0 = a0 * ild0;                            // L[lane][k]
+          const double l10 = __shfl_sync(0xffffffffu, l0, k + 1);  // L[k+1][k]
+          a1 -= l0 * l10;
+          const double d1 = __shfl_sync(0xffffffffu, a1, k + 1);
+          if (!(d1 > 0.0)) { bad = true; break; }
+          const double ild1 = rsqrt64(d1);
+          if (lane == k) invd0 = ild0;
+          if (lane == k + 1) invd0 = ild1;
+          if (in0) H[hrow(lane) + k] = l0;
+          if (in1) H[hrow(lane) + k + 1] = a1 * ild1;
+          __syncwarp();
         }
-        if (!SMALL && i1 >= k && i1 < nU) {
-          const double* rowi = H + hrow(i1);
-          acc1 = rowi[k];
+      } else {
+#pragma unroll 1
+        for (int k = 0; k < nU; ++k) {
+          double acc0 = 0.0, acc1 = 0.0;
+          const int i0 = lane, i1 = lane + 32;
+          const double* rowk = H + hrow(k);
+          if (i0 >= k && i0 < nU) {
+            const double* rowi = H + hrow(i0);
+            acc0 = rowi[k];
 #pragma unroll 4
-          for (int p = 0; p < k; ++p) acc1 -= rowi[p] * rowk[p];
+            for (int p = 0; p < k; ++p) acc0 -= rowi[p] * rowk[p];
+          }
+          if (i1 >= k && i1 < nU) {
+            const double* rowi = H + hrow(i1);
+            acc1 = rowi[k];
+#pragma unroll 4
+            for (int p = 0; p < k; ++p) acc1 -= rowi[p] * rowk[p];
+          }
+          const double d = __shfl_sync(0xffffffffu, k < 32 ? acc0 : acc1, k & 31);
+          if (!(d > 0.0)) { bad = true; break; }
+          const double ild = rsqrt64(d);
+          if (i0 == k) invd0 = ild;
+          if (i1 == k) invd1 = ild;
+          if (i0 >= k && i0 < nU) H[hrow(i0) + k] = acc0 * ild;
+          if (i1 >= k && i1 < nU) H[hrow(i1) + k] = acc1 * ild;
+          __syncwarp();
         }
-        const double d = __shfl_sync(0xffffffffu, (SMALL || k < 32) ? acc0 : acc1, k & 31);
-        if (!(d > 0.0)) { bad = true; break; }
-        const double ild = rsqrt64(d);
-        if (i0 == k) invd0 = ild;
-        if (!SMALL && i1 == k) invd1 = ild;
-        if (i0 >= k && i0 < nU) H[hrow(i0) + k] = acc0 * ild;
-        if (!SMALL && i1 >= k && i1 < nU) H[hrow(i1) + k] = acc1 * ild;
-        __syncwarp();
       }
       if (bad) { stat |= 2; break; }
 
