@@ -391,11 +391,13 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
         double acc = cv[i];
         {
           const double* hp = Hc + i * (i + 1) / 2;  // row i of the packed lower triangle, then column i below the diagonal
+          const double* hq = hp + i + i + 1;        // element (i+1, i)
+          double accq = 0.0;                        // the two parts are independent FMA chains
 #pragma unroll 2
           for (int j = 0; j <= i; ++j) acc += hp[j] * x[j];
-          hp += i + i + 1;  // element (i+1, i)
 #pragma unroll 2
-          for (int j = i + 1; j < nU; ++j) { acc += *hp * x[j]; hp += j + 1; }
+          for (int j = i + 1; j < nU; ++j) { accq += *hq * x[j]; hq += j + 1; }
+          acc += accq;
         }
         acc += cz[oBU + i] - cz[oBL + i];
         if (i >= 2) acc += cz[oRU + i - 2] - cz[oRL + i - 2];
@@ -403,8 +405,10 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
         if (TD > 0) {
           const double* fxp = F + (i >> 1) * ((i >> 1) + 1) + i;
           const double* fyp = fxp + FT;
+          double accy = 0.0;
 #pragma unroll 2
-          for (int t = i >> 1; t < T; ++t) { acc -= fxp[0] * e0[t] + fyp[0] * e1[t]; fxp += 2 * (t + 1); fyp += 2 * (t + 1); }
+          for (int t = i >> 1; t < T; ++t) { acc -= fxp[0] * e0[t]; accy -= fyp[0] * e1[t]; fxp += 2 * (t + 1); fyp += 2 * (t + 1); }
+          acc += accy;
         }
         rdU[i] = acc;
         res = fmax(res, fabs(acc));
@@ -470,11 +474,14 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
         double acc = Hc[p];
         if (TD > 0) {
           int o = (i >> 1) * ((i >> 1) + 1);  // row t = i/2 of the packed layout; j <= i < 2(t+1) so both columns exist
+          double accy = 0.0;
 #pragma unroll 2
           for (int t = i >> 1; t < T; ++t) {
-            acc += F[o + i] * Gx[o + j] + F[FT + o + i] * Gy[o + j];
+            acc += F[o + i] * Gx[o + j];
+            accy += F[FT + o + i] * Gy[o + j];
             o += 2 * (t + 1);
           }
+          acc += accy;
         }
         if (i == j) {
           acc += cz[oBU + i] * (double)cis[oBU + i] + cz[oBL + i] * (double)cis[oBL + i];
@@ -603,8 +610,10 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
             if (TD > 0) {
               const double* fxp = F + (i >> 1) * ((i >> 1) + 1) + i;
               const double* fyp = fxp + FT;
+              double accy = 0.0;
 #pragma unroll 2
-              for (int t = i >> 1; t < T; ++t) { acc += fxp[0] * e0[t] + fyp[0] * e1[t]; fxp += 2 * (t + 1); fyp += 2 * (t + 1); }
+              for (int t = i >> 1; t < T; ++t) { acc += fxp[0] * e0[t]; accy += fyp[0] * e1[t]; fxp += 2 * (t + 1); fyp += 2 * (t + 1); }
+              acc += accy;
             }
             if (sl == 0) r0 = acc; else r1 = acc;
           }
