@@ -315,6 +315,86 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------
+# --workload scan: the lidar scan -> points producer (SURVEY 8f "next" row 2), measured to the same bar
+def run_scan(args):
+    """B scans of R beams with per-beam velocities -> points for PAN (decimated to max_points = 500, C4's N).
+    metric: scans/s; roofline: HBM (a byte-moving kernel).  Algorithmic bytes per scan: 4R (ranges) + 24 (state) read,
+    per output column 8 (point) + 8 (velocity) written and 8 (velocity gather) read, 4 (count) written."""
+    import time
+
+    import torch
+
+    from neupan_b200 import _lib, scan_to_points
+    from oracle import scan as oscan
+
+    B, R, MP = args.envs or 16384, 1080, 500
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    scan = dict(angle_min=-np.pi, angle_max=np.pi, range_min=0.1, range_max=10.0)
+    off, n_sets = (0.25, 0.0, 0.1), 3
+    rng = np.random.default_rng(4321)
+    host = [dict(ranges=torch.from_numpy(rng.uniform(0.0, 11.5, size=(B, R)).astype(np.float32)).pin_memory(),
+                 velocity=torch.from_numpy(rng.uniform(-1, 1, size=(B, 2, R)).astype(np.float32)).pin_memory(),
+                 states=torch.from_numpy(np.stack([rng.uniform(-5, 5, B), rng.uniform(-5, 5, B), rng.uniform(-np.pi, np.pi, B)], 1)).pin_memory())
+            for _ in range(n_sets)]
+    devs = [{k: v.to(dev) for k, v in h.items()} for h in host]  # 3 x 212 MB of inputs: larger than the 126 MB L2
+    lib = _lib.load()
+
+    def step(i, from_host=False):
+        d = (host if from_host else devs)[i % n_sets]
+        if from_host:
+            d = {k: v.to(dev, non_blocking=True) for k, v in d.items()}
+        pts, vel, cnt = scan_to_points(d["states"], d["ranges"], scan, off, max_points=MP, velocity=d["velocity"])
+        return (pts, vel, cnt.cpu()) if from_host else (pts, vel, cnt)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    l0 = lib.nb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.nb_launch_count() - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop()
+    n_out = float(out[2].double().mean())
+    # end to end: pinned host scans in, counts read back (points stay on the device for PAN)
+    for i in range(2):
+        step(i, True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i, True)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    alg = B * (4.0 * R + 24 + n_out * 24 + 4)
+    pk = peaks()
+    roof = dict(bound="hbm", achieved=alg / (ms * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s", frac=alg / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], traffic=None,
+                kernel="scan_to_points_kernel (one CTA per scan: ballot/popc ordered compaction into a shared-memory list, FP64 transform, coalesced stores)",
+                kernel_ms=ms, share_of_step=1.0, peak_source=pk["which"], algorithmic_bytes_per_launch=alg,
+                note="the velocity array (8R B per scan) is only gathered at the kept beams; if it had to be streamed completely the bytes would be 3x")
+    line = dict(metric="lidar scans/sec -> obstacle points (batched envs)", value=B / (ms * 1e-3), unit="scans/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64 arithmetic, f32 in/out", data="synthetic",
+                config=dict(workload=f"scan: B={B} scans x R={R} beams -> max_points={MP} (decimated), velocities on", global_batch=B,
+                            l2=f"{n_sets} rotating input sets of {B * R * 12 / 1e6:.0f} MB each (> L2)"),
+                gpu_launches=int(launches), clocks=clocks, roofline=roof,
+                e2e=dict(value=B / (e2e_ms * 1e-3), unit="scans/s", h2d_bytes_per_step=int(B * (R * 12 + 24)), d2h_bytes_per_step=int(B * 4), ms_per_step=e2e_ms,
+                         api="neupan_b200.scan_to_points on pinned host tensors (points stay on the device for PAN.forward)"))
+    if not args.no_cpu:
+        n = 64
+        t0 = time.perf_counter()
+        oscan.scan_batch(host[0]["states"].numpy()[:n], host[0]["ranges"].numpy()[:n], scan, off, max_points=MP, velocity=host[0]["velocity"].numpy()[:n])
+        wall = time.perf_counter() - t0
+        line["cpu_baseline"] = dict(value=n / wall, unit="scans/s", cores=1, kind="port", sample=f"{n} scans, {wall:.1f} s wall; oracle/scan.py (the reference's per-beam Python loop restated)")
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -328,7 +408,28 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, help="env sub-batches pipelined on internal streams (NB_OPT_OVERLAP)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload == "scan" and args.impl == "ours":
+        run_scan(args)
+    elif args.workload == "scan":  # CPU arm of the scan stage: the per-beam loop of the reference, restated (oracle/scan.py)
+        from oracle import scan as oscan
+        rng = np.random.default_rng(4321)
+        n, R, MP = 64, 1080, 500
+        scan = dict(angle_min=-np.pi, angle_max=np.pi, range_min=0.1, range_max=10.0)
+        ranges, vel = rng.uniform(0.0, 11.5, size=(n, R)).astype(np.float32), rng.uniform(-1, 1, size=(n, 2, R)).astype(np.float32)
+        states = np.stack([rng.uniform(-5, 5, n), rng.uniform(-5, 5, n), rng.uniform(-np.pi, np.pi, n)], 1)
+        times = []
+        for _ in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            oscan.scan_batch(states, ranges, scan, (0.25, 0.0, 0.1), max_points=MP, velocity=vel)
+            times.append(time.perf_counter() - t0)
+        dt = float(np.mean(times[args.warmup:]))
+        v = n / dt
+        print(json.dumps(dict(metric="lidar scans/sec -> obstacle points (batched envs)", value=v, unit="scans/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
+                              ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                              config=dict(workload=f"scan: R={R} beams -> max_points={MP}", scans_per_step=n),
+                              cpu_baseline=dict(value=v, unit="scans/s", cores=1, kind="port", sample=f"{n} scans/step; oracle/scan.py (per-beam Python loop of neupan.py:173-281)"),
+                              e2e=dict(value=v, unit="scans/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

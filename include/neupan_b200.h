@@ -149,6 +149,29 @@ int nb_nrmp_forward(nb_pan_t* pan, int32_t B, const float* nom_s, const float* n
                     const float* ref_us, const float* fa, const float* fb,
                     float* out_s, float* out_u, float* out_d, int32_t* out_status, void* stream);
 
+/* ---- lidar scan -> obstacle points (the producer of `points`; SURVEY 8f "next" row 2) -------------------------- */
+
+/* The `scan` dict and the arguments of neupan.scan_to_point / scan_to_point_velocity (neupan/neupan.py:173-281). */
+typedef struct nb_scan_config {
+  double angle_min, angle_max;   /* scan["angle_min"], scan["angle_max"]: beam i sits at linspace(min, max, R)[i]      */
+  double range_min, range_max;   /* kept: range < range_max - 0.02 and range > (mode 1: >=) range_min                  */
+  double scan_offset[3];         /* sensor pose in the robot frame                                                     */
+  double angle_range[2];         /* kept: angle_range[0] < angle < angle_range[1]                                      */
+  int32_t down_sample;           /* the [:, ::down_sample] stride over the kept points (>= 1)                          */
+  int32_t velocity_mode;         /* 0: scan_to_point (offset applied as s_R p + s_t, neupan.py:216-217);
+                                    1: scan_to_point_velocity (s_R^T (p - s_t), range >= range_min, neupan.py:258-273) */
+} nb_scan_config;
+
+/* B scans of R beams each -> points (B,2,max_points) float32 in the world frame, their per-beam velocities (optional)
+ * and the number of valid columns per environment; more than max_points survivors are decimated exactly like
+ * PAN.generate_point_flow does (pan.py:171-174 -> downsample_decimation: columns linspace(0, n-1, max_points).astype(int)).
+ * All pointers are DEVICE pointers; ranges (B,R) float32, velocity (B,2,R) float32 or NULL, states (B,3) float64
+ * [x, y, theta].  The outputs are exactly what nb_pan_forward takes as (points, velocities, num_points) with N = max_points.
+ * A scan with no surviving beam yields count 0 (the reference returns None). */
+int nb_scan_to_points(int32_t B, int32_t R, const float* ranges, const float* velocity, const double* states,
+                      const nb_scan_config* cfg, int32_t max_points, float* points, float* velocities_out,
+                      int32_t* counts, void* stream);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t nb_launch_count(void);
 const char* nb_last_error(void);

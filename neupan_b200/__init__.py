@@ -9,6 +9,7 @@ from . import configuration, util
 from .robot import robot
 from .blocks import DUNE, NRMP, PAN, InitialPath, ObsPointNet
 from .neupan import neupan
+from .scan import scan_to_points
 
-__all__ = ["configuration", "util", "robot", "neupan", "PAN", "DUNE", "NRMP", "ObsPointNet", "InitialPath"]
+__all__ = ["configuration", "util", "robot", "neupan", "PAN", "DUNE", "NRMP", "ObsPointNet", "InitialPath", "scan_to_points"]
 __version__ = "0.1.0"

@@ -33,6 +33,15 @@ class PanConfig(C.Structure):
     ]
 
 
+class ScanConfig(C.Structure):
+    """struct nb_scan_config (include/neupan_b200.h)."""
+    _fields_ = [
+        ("angle_min", C.c_double), ("angle_max", C.c_double), ("range_min", C.c_double), ("range_max", C.c_double),
+        ("scan_offset", C.c_double * 3), ("angle_range", C.c_double * 2),
+        ("down_sample", C.c_int32), ("velocity_mode", C.c_int32),
+    ]
+
+
 _FP = C.c_void_p  # device or host float* / int32*: passed as raw addresses
 
 # name -> (restype, argtypes); every symbol include/neupan_b200.h declares
@@ -50,6 +59,7 @@ SYMBOLS = {
     "nb_pan_read_diagnostics": (C.c_int, [C.c_void_p, C.c_int32, _FP, C.c_void_p]),
     "nb_dune_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [_FP] * 5 + [C.c_void_p]),
     "nb_nrmp_forward": (C.c_int, [C.c_void_p, C.c_int32] + [_FP] * 10 + [C.c_void_p]),
+    "nb_scan_to_points": (C.c_int, [C.c_int32, C.c_int32, _FP, _FP, _FP, C.POINTER(ScanConfig), C.c_int32, _FP, _FP, _FP, C.c_void_p]),
     "nb_launch_count": (C.c_int64, []),
     "nb_last_error": (C.c_char_p, []),
     "nb_version": (C.c_int, []),

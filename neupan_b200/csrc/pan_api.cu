@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "dune_launch.cuh"
 #include "nrmp_kernel.cuh"
+#include "scan_kernel.cuh"
 
 #include <vector>
 
@@ -519,6 +520,31 @@ int nb_pan_forward_host(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, c
   if (out_iters) NB_CUDA(d2h(out_iters, p->h_io, (size_t)B * 4));
   if (out_status) NB_CUDA(d2h(out_status, p->h_io + p->cfg.max_envs, (size_t)B * 4));
   NB_CUDA(cudaStreamSynchronize(st));
+  return NB_OK;
+}
+
+int nb_scan_to_points(int32_t B, int32_t R, const float* ranges, const float* velocity, const double* states,
+                      const nb_scan_config* cfg, int32_t max_points, float* points, float* velocities_out,
+                      int32_t* counts, void* stream) {
+  if (!cfg || !ranges || !states || !points || !counts) return fail(NB_ERR_INVALID, "nb_scan_to_points: null argument");
+  if (B < 0 || R < 1 || max_points < 1) return fail(NB_ERR_INVALID, "nb_scan_to_points: B=%d R=%d max_points=%d", B, R, max_points);
+  if (cfg->down_sample < 1) return fail(NB_ERR_INVALID, "down_sample must be >= 1 (got %d)", cfg->down_sample);
+  if ((size_t)R * sizeof(int32_t) > 200 * 1024) return fail(NB_ERR_CAPACITY, "R=%d beams exceed the shared-memory list (51200)", R);
+  if (B == 0) return NB_OK;
+  nb::ScanParams prm;
+  prm.B = B; prm.R = R; prm.max_points = max_points;
+  prm.ranges = ranges; prm.velocity = velocity; prm.states = states;
+  prm.angle_min = cfg->angle_min; prm.angle_max = cfg->angle_max; prm.range_min = cfg->range_min; prm.range_max = cfg->range_max;
+  prm.off_x = cfg->scan_offset[0]; prm.off_y = cfg->scan_offset[1]; prm.off_th = cfg->scan_offset[2];
+  prm.angle_lo = cfg->angle_range[0]; prm.angle_hi = cfg->angle_range[1];
+  prm.down_sample = cfg->down_sample; prm.velocity_mode = cfg->velocity_mode ? 1 : 0;
+  prm.points = points; prm.vel_out = velocities_out; prm.counts = counts;
+  const size_t smem = (size_t)R * sizeof(int32_t);
+  if (smem > 48 * 1024) NB_CUDA(cudaFuncSetAttribute(nb::scan_to_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = R >= 256 ? 256 : (R >= 128 ? 128 : 64);
+  nb::scan_to_points_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(prm);
+  ++g_launches;
+  NB_CUDA(cudaGetLastError());
   return NB_OK;
 }
 
