@@ -387,7 +387,7 @@ def run_scan(args):
                 e2e=dict(value=B / (e2e_ms * 1e-3), unit="scans/s", h2d_bytes_per_step=int(B * (R * 12 + 24)), d2h_bytes_per_step=int(B * 4), ms_per_step=e2e_ms,
                          api="neupan_b200.scan_to_points on pinned host tensors (points stay on the device for PAN.forward)"))
     if not args.no_cpu:
-        n = 64
+        n = min(B, 4096)
         t0 = time.perf_counter()
         oscan.scan_batch(host[0]["states"].numpy()[:n], host[0]["ranges"].numpy()[:n], scan, off, max_points=MP, velocity=host[0]["velocity"].numpy()[:n])
         wall = time.perf_counter() - t0

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -540,9 +541,16 @@ int nb_scan_to_points(int32_t B, int32_t R, const float* ranges, const float* ve
   prm.down_sample = cfg->down_sample; prm.velocity_mode = cfg->velocity_mode ? 1 : 0;
   prm.points = points; prm.vel_out = velocities_out; prm.counts = counts;
   const size_t smem = (size_t)R * sizeof(int32_t);
-  if (smem > 48 * 1024) NB_CUDA(cudaFuncSetAttribute(nb::scan_to_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int threads = R >= 256 ? 256 : (R >= 128 ? 128 : 64);
-  nb::scan_to_points_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(prm);
+  static const bool generic_only = getenv("NB_SCAN_GENERIC") != nullptr;  // developer switch: force the chunked kernel
+  if (R <= nb::kScanMaxChunks * 1024 && !generic_only) {  // all ranges of a thread in registers, one barrier
+    int threads = 128;
+    while (threads * nb::kScanMaxChunks < R) threads *= 2;
+    if (R >= 512 && threads < 256) threads = 256;
+    nb::scan_to_points_fast_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(prm);
+  } else {
+    if (smem > 48 * 1024) NB_CUDA(cudaFuncSetAttribute(nb::scan_to_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nb::scan_to_points_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(prm);
+  }
   ++g_launches;
   NB_CUDA(cudaGetLastError());
   return NB_OK;

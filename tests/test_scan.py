@@ -92,6 +92,32 @@ def test_kernel_matches_reference_golden_vectors(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("R,mp,ds,vm", [(9000, 300, 1, True), (8192, 8192, 2, False), (40, 40, 1, True), (33, 7, 1, False), (2049, 500, 3, True)])
+def test_kernel_matches_oracle_at_other_beam_counts(R, mp, ds, vm):
+    """R = 9000 runs the chunked (generic) kernel, the others the register-resident one at 128 ... 1024 threads."""
+    import torch
+
+    from neupan_b200 import scan_to_points
+
+    B = 2
+    rng = np.random.default_rng(R)
+    scan = dict(angle_min=-3.0, angle_max=3.1, range_min=0.3, range_max=9.0)
+    ranges = rng.uniform(0.0, 10.0, size=(B, R)).astype(np.float32)
+    velocity = rng.normal(size=(B, 2, R)).astype(np.float32)
+    states = np.stack([rng.uniform(-5, 5, B), rng.uniform(-5, 5, B), rng.uniform(-np.pi, np.pi, B)], 1)
+    off, ar = (0.2, -0.3, 0.5), (-2.9, 3.0)
+    want_p, want_v, want_c = oscan.scan_batch(states, ranges, scan, off, ar, ds, mp, velocity if vm else None, vm)
+    pts, vel, cnt = scan_to_points(torch.from_numpy(states), torch.from_numpy(ranges), scan, off, ar, ds, mp, torch.from_numpy(velocity) if vm else None, vm)
+    cnt = cnt.cpu().numpy()
+    assert np.array_equal(cnt, want_c)
+    for b in range(B):
+        a, w = pts.cpu().numpy()[b, :, :cnt[b]], want_p[b, :, :cnt[b]]
+        assert np.all(np.abs(a - w) <= np.spacing(np.abs(w).astype(np.float32)))
+        if vm:
+            assert np.array_equal(vel.cpu().numpy()[b, :, :cnt[b]], want_v[b, :, :cnt[b]])
+
+
+@pytest.mark.gpu
 def test_kernel_output_feeds_pan_forward_like_the_host_path():
     """scan -> points on the GPU -> PAN.forward(num_points=counts) == host scan_to_point_velocity -> PAN.forward per env."""
     import dataclasses
