@@ -172,6 +172,56 @@ int nb_scan_to_points(int32_t B, int32_t R, const float* ranges, const float* ve
                       const nb_scan_config* cfg, int32_t max_points, float* points, float* velocities_out,
                       int32_t* counts, void* stream);
 
+/* ---- initial path: check_arrive + generate_nom_ref_state for B environments (SURVEY 8f "next" row 1) -------------- */
+
+/* The numbers of InitialPath.__init__ (neupan/blocks/initial_path.py:35-64) the per-step work needs. */
+typedef struct nb_ipath_config {
+  int32_t receding;                /* T */
+  int32_t kinematics;              /* NB_KIN_*: selects the motion_predict_model (initial_path.py:386-444) */
+  int32_t loop;                    /* restart at the first curve when the last one is finished (:262-269) */
+  int32_t ind_range;               /* window of closest_point (:166-183), reference default 10 */
+  int32_t arrive_index_threshold;  /* check_curve_arrive (:282-290), reference default 1 */
+  int32_t max_envs;
+  int32_t device;
+  int32_t reserved_;
+  double step_time;
+  double wheelbase;                /* robot.L, acker only */
+  double arrive_threshold;         /* reference default 0.1 */
+  double close_threshold;          /* reference default 0.1 */
+} nb_ipath_config;
+
+typedef struct nb_ipath nb_ipath_t;
+
+int nb_ipath_create(const nb_ipath_config* cfg, nb_ipath_t** out);
+int nb_ipath_destroy(nb_ipath_t* ip);
+
+/* InitialPath.set_initial_path (initial_path.py:128-144) for B environments, already split by gear
+ * (split_path_with_gear, :294-317): HOST arrays; points (P,4) float64 rows [x, y, theta, gear], all curves of all
+ * environments back to back; curve_begin (C+1) offsets into points; env_curve_begin (B+1) offsets into curve_begin;
+ * interval (B) = cal_average_interval of each environment's whole path (:146-164; computed by the caller, whose
+ * math.hypot it must reproduce).  Resets curve_index / point_index / arrive_flag.  The handle keeps a MUTABLE device copy
+ * of the points: like the reference it rewrites path headings while generating references (:99,112,191-192). */
+int nb_ipath_set_paths(nb_ipath_t* ip, int32_t B, const double* points, int64_t P, const int32_t* curve_begin, int32_t C,
+                       const int32_t* env_curve_begin, const double* interval);
+
+/* One control step for B environments (neupan.forward before PAN, neupan/neupan.py:114-121):
+ *   arrived[b] = InitialPath.check_arrive(state_b)                              (initial_path.py:251-292)
+ *   nom_s, nom_u, ref_s, ref_us = InitialPath.generate_nom_ref_state(state_b, cur_vel_b, ref_speed)   (:68-126)
+ * DEVICE pointers: states (B,3) float64; cur_vel (B,2,T) float32 (the velocities PAN returned at the previous step);
+ * outputs float32 in nb_pan_forward's layouts: nom_s (B,3,T+1), nom_u (B,2,T), ref_s (B,3,T+1), ref_us (B,T);
+ * arrived (B) int32.  Environments that have arrived get zero trajectories (the reference returns before generating). */
+int nb_ipath_step(nb_ipath_t* ip, int32_t B, const double* states, const float* cur_vel, double ref_speed,
+                  float* nom_s, float* nom_u, float* ref_s, float* ref_us, int32_t* arrived, void* stream);
+
+/* neupan.reset (neupan/neupan.py:287-294): point_index = curve_index = 0, arrive_flag = False for every environment.
+ * The path headings rewritten so far stay as they are (as in the reference). */
+int nb_ipath_reset(nb_ipath_t* ip);
+
+/* Persistent per-environment indices and a copy of the (mutated) path points; any pointer may be NULL.  DEVICE pointers
+ * for the indices (B) int32, HOST pointer for points (P,4) float64 (synchronises `stream`). */
+int nb_ipath_read_state(nb_ipath_t* ip, int32_t B, int32_t* curve_index, int32_t* point_index, int32_t* arrive_flag,
+                        double* points_host, void* stream);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t nb_launch_count(void);
 const char* nb_last_error(void);

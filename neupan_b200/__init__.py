@@ -10,6 +10,7 @@ from .robot import robot
 from .blocks import DUNE, NRMP, PAN, InitialPath, ObsPointNet
 from .neupan import neupan
 from .scan import scan_to_points
+from .ipath import InitialPathBatch
 
-__all__ = ["configuration", "util", "robot", "neupan", "PAN", "DUNE", "NRMP", "ObsPointNet", "InitialPath", "scan_to_points"]
+__all__ = ["configuration", "util", "robot", "neupan", "PAN", "DUNE", "NRMP", "ObsPointNet", "InitialPath", "scan_to_points", "InitialPathBatch"]
 __version__ = "0.1.0"

@@ -42,6 +42,15 @@ class ScanConfig(C.Structure):
     ]
 
 
+class IpathConfig(C.Structure):
+    """struct nb_ipath_config (include/neupan_b200.h)."""
+    _fields_ = [
+        ("receding", C.c_int32), ("kinematics", C.c_int32), ("loop", C.c_int32), ("ind_range", C.c_int32),
+        ("arrive_index_threshold", C.c_int32), ("max_envs", C.c_int32), ("device", C.c_int32), ("reserved_", C.c_int32),
+        ("step_time", C.c_double), ("wheelbase", C.c_double), ("arrive_threshold", C.c_double), ("close_threshold", C.c_double),
+    ]
+
+
 _FP = C.c_void_p  # device or host float* / int32*: passed as raw addresses
 
 # name -> (restype, argtypes); every symbol include/neupan_b200.h declares
@@ -60,6 +69,12 @@ SYMBOLS = {
     "nb_dune_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [_FP] * 5 + [C.c_void_p]),
     "nb_nrmp_forward": (C.c_int, [C.c_void_p, C.c_int32] + [_FP] * 10 + [C.c_void_p]),
     "nb_scan_to_points": (C.c_int, [C.c_int32, C.c_int32, _FP, _FP, _FP, C.POINTER(ScanConfig), C.c_int32, _FP, _FP, _FP, C.c_void_p]),
+    "nb_ipath_create": (C.c_int, [C.POINTER(IpathConfig), C.POINTER(C.c_void_p)]),
+    "nb_ipath_destroy": (C.c_int, [C.c_void_p]),
+    "nb_ipath_set_paths": (C.c_int, [C.c_void_p, C.c_int32, _FP, C.c_int64, _FP, C.c_int32, _FP, _FP]),
+    "nb_ipath_step": (C.c_int, [C.c_void_p, C.c_int32, _FP, _FP, C.c_double, _FP, _FP, _FP, _FP, _FP, C.c_void_p]),
+    "nb_ipath_reset": (C.c_int, [C.c_void_p]),
+    "nb_ipath_read_state": (C.c_int, [C.c_void_p, C.c_int32, _FP, _FP, _FP, _FP, C.c_void_p]),
     "nb_launch_count": (C.c_int64, []),
     "nb_last_error": (C.c_char_p, []),
     "nb_version": (C.c_int, []),

@@ -13,6 +13,7 @@
 #include "dune_launch.cuh"
 #include "nrmp_kernel.cuh"
 #include "scan_kernel.cuh"
+#include "ipath_kernel.cuh"
 
 #include <vector>
 
@@ -51,6 +52,19 @@ cudaError_t dalloc(T** p, size_t n) {
 }
 
 }  // namespace
+
+struct nb_ipath {
+  nb_ipath_config cfg;
+  int B = 0;
+  int64_t P = 0;
+  double* d_pts = nullptr;
+  int32_t* d_curve_begin = nullptr;
+  int32_t* d_env_curve_begin = nullptr;
+  double* d_interval = nullptr;
+  int32_t* d_curve_index = nullptr;
+  int32_t* d_point_index = nullptr;
+  int32_t* d_arrive_flag = nullptr;
+};
 
 struct nb_pan {
   nb_pan_config cfg;
@@ -553,6 +567,112 @@ int nb_scan_to_points(int32_t B, int32_t R, const float* ranges, const float* ve
   }
   ++g_launches;
   NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+
+// ---- initial path ---------------------------------------------------------------------------------
+int nb_ipath_create(const nb_ipath_config* cfg, nb_ipath_t** out) {
+  if (!cfg || !out) return fail(NB_ERR_INVALID, "nb_ipath_create: null argument");
+  if (cfg->receding < 1 || cfg->receding > nb::kIpathMaxT) return fail(NB_ERR_INVALID, "receding = %d outside [1, %d]", cfg->receding, nb::kIpathMaxT);
+  if (cfg->kinematics < 0 || cfg->kinematics > 2) return fail(NB_ERR_INVALID, "kinematics currently only supports diff, acker or omni");
+  if (cfg->kinematics == NB_KIN_ACKER && !(cfg->wheelbase > 0)) return fail(NB_ERR_INVALID, "acker needs a positive wheelbase");
+  if (cfg->max_envs < 1 || !(cfg->step_time > 0)) return fail(NB_ERR_INVALID, "max_envs / step_time must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev)
+    return fail(NB_ERR_NO_DEVICE, "no CUDA device available: neupan_b200 has no CPU fallback");
+  NB_CUDA(cudaSetDevice(cfg->device));
+  nb_ipath* p = new nb_ipath();
+  p->cfg = *cfg;
+  cudaError_t e = dalloc(&p->d_env_curve_begin, (size_t)cfg->max_envs + 1);
+  if (e == cudaSuccess) e = dalloc(&p->d_interval, (size_t)cfg->max_envs);
+  if (e == cudaSuccess) e = dalloc(&p->d_curve_index, (size_t)cfg->max_envs);
+  if (e == cudaSuccess) e = dalloc(&p->d_point_index, (size_t)cfg->max_envs);
+  if (e == cudaSuccess) e = dalloc(&p->d_arrive_flag, (size_t)cfg->max_envs);
+  if (e != cudaSuccess) {
+    nb_ipath_destroy(p);
+    return fail(NB_ERR_CUDA, "nb_ipath_create: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return NB_OK;
+}
+
+int nb_ipath_destroy(nb_ipath_t* p) {
+  if (!p) return NB_OK;
+  cudaSetDevice(p->cfg.device);
+  void* bufs[] = {p->d_pts, p->d_curve_begin, p->d_env_curve_begin, p->d_interval, p->d_curve_index, p->d_point_index, p->d_arrive_flag};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  delete p;
+  return NB_OK;
+}
+
+int nb_ipath_reset(nb_ipath_t* p) {
+  if (!p) return fail(NB_ERR_INVALID, "nb_ipath_reset: null handle");
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  NB_CUDA(cudaMemset(p->d_curve_index, 0, sizeof(int32_t) * p->cfg.max_envs));
+  NB_CUDA(cudaMemset(p->d_point_index, 0, sizeof(int32_t) * p->cfg.max_envs));
+  NB_CUDA(cudaMemset(p->d_arrive_flag, 0, sizeof(int32_t) * p->cfg.max_envs));
+  return NB_OK;
+}
+
+int nb_ipath_set_paths(nb_ipath_t* p, int32_t B, const double* points, int64_t P, const int32_t* curve_begin, int32_t C,
+                       const int32_t* env_curve_begin, const double* interval) {
+  if (!p || !points || !curve_begin || !env_curve_begin || !interval) return fail(NB_ERR_INVALID, "nb_ipath_set_paths: null argument");
+  if (B < 1 || B > p->cfg.max_envs) return fail(NB_ERR_CAPACITY, "B = %d outside [1, max_envs = %d]", B, p->cfg.max_envs);
+  if (P < 1 || C < B) return fail(NB_ERR_INVALID, "every environment needs at least one curve with one point (P = %lld, C = %d)", (long long)P, C);
+  if (env_curve_begin[0] != 0 || env_curve_begin[B] != C || curve_begin[0] != 0 || curve_begin[C] != P)
+    return fail(NB_ERR_INVALID, "curve_begin / env_curve_begin do not cover the points");
+  for (int b = 0; b < B; ++b)
+    if (env_curve_begin[b + 1] <= env_curve_begin[b]) return fail(NB_ERR_INVALID, "environment %d has no curve", b);
+  for (int c = 0; c < C; ++c)
+    if (curve_begin[c + 1] <= curve_begin[c]) return fail(NB_ERR_INVALID, "curve %d is empty", c);
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  if (p->d_pts) cudaFree(p->d_pts);
+  if (p->d_curve_begin) cudaFree(p->d_curve_begin);
+  p->d_pts = nullptr; p->d_curve_begin = nullptr;
+  NB_CUDA(dalloc(&p->d_pts, (size_t)P * 4));
+  NB_CUDA(dalloc(&p->d_curve_begin, (size_t)C + 1));
+  NB_CUDA(cudaMemcpy(p->d_pts, points, sizeof(double) * 4 * P, cudaMemcpyHostToDevice));
+  NB_CUDA(cudaMemcpy(p->d_curve_begin, curve_begin, sizeof(int32_t) * (C + 1), cudaMemcpyHostToDevice));
+  NB_CUDA(cudaMemcpy(p->d_env_curve_begin, env_curve_begin, sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice));
+  NB_CUDA(cudaMemcpy(p->d_interval, interval, sizeof(double) * B, cudaMemcpyHostToDevice));
+  p->B = B; p->P = P;
+  return nb_ipath_reset(p);
+}
+
+int nb_ipath_step(nb_ipath_t* p, int32_t B, const double* states, const float* cur_vel, double ref_speed,
+                  float* nom_s, float* nom_u, float* ref_s, float* ref_us, int32_t* arrived, void* stream) {
+  if (!p || !states || !cur_vel || !nom_s || !nom_u || !ref_s || !ref_us || !arrived) return fail(NB_ERR_INVALID, "nb_ipath_step: null argument");
+  if (!p->d_pts) return fail(NB_ERR_INVALID, "initial path is not set (nb_ipath_set_paths)");
+  if (B != p->B) return fail(NB_ERR_INVALID, "B = %d but the paths were set for %d environments", B, p->B);
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  nb::IpathParams prm;
+  prm.B = B; prm.T = p->cfg.receding; prm.kinematics = p->cfg.kinematics; prm.loop = p->cfg.loop;
+  prm.ind_range = p->cfg.ind_range; prm.arrive_index_threshold = p->cfg.arrive_index_threshold;
+  prm.dt = p->cfg.step_time; prm.L = p->cfg.wheelbase; prm.arrive_threshold = p->cfg.arrive_threshold; prm.close_threshold = p->cfg.close_threshold;
+  prm.ref_speed = ref_speed;
+  prm.pts = p->d_pts; prm.curve_begin = p->d_curve_begin; prm.env_curve_begin = p->d_env_curve_begin; prm.interval = p->d_interval;
+  prm.curve_index = p->d_curve_index; prm.point_index = p->d_point_index; prm.arrive_flag = p->d_arrive_flag;
+  prm.states = states; prm.cur_vel = cur_vel; prm.nom_s = nom_s; prm.nom_u = nom_u; prm.ref_s = ref_s; prm.ref_us = ref_us; prm.arrived = arrived;
+  nb::ipath_step_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(prm);
+  ++g_launches;
+  NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+
+int nb_ipath_read_state(nb_ipath_t* p, int32_t B, int32_t* curve_index, int32_t* point_index, int32_t* arrive_flag,
+                        double* points_host, void* stream) {
+  if (!p) return fail(NB_ERR_INVALID, "nb_ipath_read_state: null handle");
+  if (B != p->B) return fail(NB_ERR_INVALID, "B = %d but the paths were set for %d environments", B, p->B);
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (curve_index) NB_CUDA(cudaMemcpyAsync(curve_index, p->d_curve_index, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+  if (point_index) NB_CUDA(cudaMemcpyAsync(point_index, p->d_point_index, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+  if (arrive_flag) NB_CUDA(cudaMemcpyAsync(arrive_flag, p->d_arrive_flag, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+  if (points_host) {
+    NB_CUDA(cudaMemcpyAsync(points_host, p->d_pts, sizeof(double) * 4 * p->P, cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaStreamSynchronize(st));
+  }
   return NB_OK;
 }
 
