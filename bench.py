@@ -395,6 +395,102 @@ def run_scan(args):
     print(json.dumps(line))
 
 
+# --------------------------------------------------------------------------------------------
+# --workload ipath: check_arrive + generate_nom_ref_state for B robots (SURVEY 8f "next" row 1)
+def run_ipath(args):
+    """metric: env path-steps/s.  Algorithmic bytes per env and step: 24 (state) + 8T (velocities) read, the path points the
+    step touches (closest-point window + T reference points, 32 B each) read, 4(3(T+1)) x 2 + 4(2T) + 4T + 12 written."""
+    import time
+
+    import torch
+
+    from neupan_b200 import InitialPathBatch, _lib
+    from oracle import ipath as oip
+
+    B, T, NPTS = args.envs or 16384, 10, 200
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    rng = np.random.default_rng(99)
+
+    def path(b):
+        pts, x, y, th = np.empty((NPTS, 4)), 0.0, 0.0, 0.3
+        step, curve = 0.4 + 0.0002 * ((b % 5) - 2), 0.02 * ((b % 7) - 3)
+        for i in range(NPTS):
+            pts[i] = (x, y, th, 1.0 if i < 150 else -1.0)
+            g = pts[i, 3]
+            x += step * np.cos(th) * g; y += step * np.sin(th) * g; th += curve
+        return pts
+
+    protos = [path(b) for b in range(35)]
+    paths = [protos[b % 35] for b in range(B)]
+    ipb = InitialPathBatch(T, 0.1, "diff", max_envs=B, device=dev)
+    ipb.set_initial_paths(paths)
+    lib = _lib.load()
+    n_sets = 4
+    sets = []
+    for s in range(n_sets):
+        k = rng.integers(0, 120, B)
+        st = np.stack([np.array([protos[b % 35][k[b], 0], protos[b % 35][k[b], 1], protos[b % 35][k[b], 2]]) for b in range(B)]) + rng.normal(0, 0.02, (B, 3))
+        vel = rng.uniform(-1, 1, (B, 2, T)).astype(np.float32); vel[:, 0] += 3.0
+        sets.append((torch.from_numpy(st).pin_memory(), torch.from_numpy(vel).pin_memory()))
+    dsets = [(a.to(dev), b.to(dev)) for a, b in sets]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(i, host=False):
+        a, b = (sets if host else dsets)[i % n_sets]
+        if host:
+            a, b = a.to(dev, non_blocking=True), b.to(dev, non_blocking=True)
+        out = ipb.step(a, b, 4.0)
+        return out[4].cpu() if host else out
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    l0, tot = lib.nb_launch_count(), 0.0
+    for i in range(args.steps):
+        flush.zero_()  # the path window of an env is re-read every step: flush L2 between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); step(i); e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    launches = lib.nb_launch_count() - l0
+    ms = tot / args.steps
+    clocks = sampler.stop()
+    step(0, True); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i, True)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    alg = B * (24 + 8.0 * T + 32.0 * (10 + T) + 4.0 * (6 * (T + 1) + 2 * T + T) + 12)
+    pk = peaks()
+    roof = dict(bound="hbm", achieved=alg / (ms * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s", frac=alg / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], traffic=None,
+                kernel="ipath_step_kernel (one thread per environment: sequential closest-point window + T-step rollout / reference walk in FP64)",
+                kernel_ms=ms, share_of_step=1.0, peak_source=pk["which"], algorithmic_bytes_per_launch=alg,
+                note="latency-bound sequential per-environment logic with FP64 trigonometry; ~1 KB of traffic per environment")
+    line = dict(metric="initial-path steps/sec (check_arrive + generate_nom_ref_state, batched envs)", value=B / (ms * 1e-3), unit="env-steps/s", n_gpus=1,
+                steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64 arithmetic, f32 out",
+                data="synthetic", config=dict(workload=f"ipath: B={B} envs, T={T}, paths of {NPTS} points with a gear switch", global_batch=B, l2="L2 flushed between timed iterations"),
+                gpu_launches=int(launches), clocks=clocks, roofline=roof,
+                e2e=dict(value=B / (e2e_ms * 1e-3), unit="env-steps/s", h2d_bytes_per_step=int(B * (24 + 8 * T)), d2h_bytes_per_step=int(B * 4), ms_per_step=e2e_ms,
+                         api="neupan_b200.InitialPathBatch.step on pinned host tensors (trajectories stay on the device for PAN.forward)"))
+    if not args.no_cpu:
+        n = 512
+        os_ = [oip.OracleInitialPath(T, 0.1, "diff") for _ in range(n)]
+        for b, o in enumerate(os_):
+            o.set_initial_path([r.reshape(4, 1).copy() for r in protos[b % 35]])
+        st, vel = sets[0][0].numpy(), sets[0][1].numpy().astype(np.float64)
+        t0 = time.perf_counter()
+        for b, o in enumerate(os_):
+            if not o.check_arrive(st[b].reshape(3, 1)):
+                o.generate_nom_ref_state(st[b].reshape(3, 1), vel[b], 4.0)
+        wall = time.perf_counter() - t0
+        line["cpu_baseline"] = dict(value=n / wall, unit="env-steps/s", cores=1, kind="port", sample=f"{n} envs, {wall:.2f} s wall; oracle/ipath.py (the reference's numpy code restated)")
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -408,7 +504,9 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, help="env sub-batches pipelined on internal streams (NB_OPT_OVERLAP)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.workload == "scan" and args.impl == "ours":
+    if args.workload == "ipath" and args.impl == "ours":
+        run_ipath(args)
+    elif args.workload == "scan" and args.impl == "ours":
         run_scan(args)
     elif args.workload == "scan":  # CPU arm of the scan stage: the per-beam loop of the reference, restated (oracle/scan.py)
         from oracle import scan as oscan
