@@ -48,8 +48,9 @@ def drive(ip, path, seed, record):
     ip.set_initial_path([p.copy() for p in path])
     state = np.array([[0.05], [-0.03], [0.25]])
     for k in range(STEPS):
-        vel = rng.uniform(-1, 1, (2, T)).astype(np.float32).astype(np.float64)
+        vel = rng.uniform(-1, 1, (2, T))
         vel[0] += 3.0
+        vel = vel.astype(np.float32).astype(np.float64)  # what PAN hands back (float32), held in the float64 array numpy computes with
         arrived = bool(ip.check_arrive(state))
         out = None if arrived else ip.generate_nom_ref_state(state, vel, REF_SPEED)
         record(k, state, vel, arrived, out, ip.point_index, ip.curve_index)
