@@ -11,6 +11,7 @@ from .blocks import DUNE, NRMP, PAN, InitialPath, ObsPointNet
 from .neupan import neupan
 from .scan import scan_to_points
 from .ipath import InitialPathBatch
+from .planner_batch import PlannerBatch
 
-__all__ = ["configuration", "util", "robot", "neupan", "PAN", "DUNE", "NRMP", "ObsPointNet", "InitialPath", "scan_to_points", "InitialPathBatch"]
+__all__ = ["configuration", "util", "robot", "neupan", "PAN", "DUNE", "NRMP", "ObsPointNet", "InitialPath", "scan_to_points", "InitialPathBatch", "PlannerBatch"]
 __version__ = "0.1.0"
