@@ -491,6 +491,85 @@ def run_ipath(args):
     print(json.dumps(line))
 
 
+# --------------------------------------------------------------------------------------------
+# --workload control: the whole control step of B robots on the device (PlannerBatch = ipath -> scan -> PAN)
+def run_control(args):
+    """C4's robot / adjust values and B = 4096, K = 10, T = 10; obstacles arrive as lidar scans (R = 1080 beams with per-beam
+    velocities, decimated to 500 points).  value: device-timed with scans and states resident; e2e: pinned host states + scans in,
+    actions out."""
+    import time
+
+    import torch
+
+    from helpers import CONFIGS, weights_path
+    from neupan_b200 import PlannerBatch, _lib
+
+    cfg = CONFIGS["C4"]
+    B, R, N = args.envs or cfg.B, 1080, cfg.N
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    rng = np.random.default_rng(2024)
+    pl = PlannerBatch(B, cfg.T, cfg.dt, 4.0, robot_kwargs=cfg.robot_kwargs, adjust_kwargs=dict(cfg.adjust), device=dev,
+                      pan_kwargs=dict(iter_num=cfg.K, dune_max_num=N, nrmp_max_num=cfg.M, dune_checkpoint=weights_path(cfg.model), iter_threshold=0.0, max_points=N))
+
+    def path(j):
+        pts, x, y, th = np.empty((150, 4)), 0.0, 0.0, 0.3
+        for i in range(150):
+            pts[i] = (x, y, th, 1.0)
+            x += 0.4 * np.cos(th); y += 0.4 * np.sin(th); th += 0.004 * (j - 8)
+        return pts
+
+    protos = [path(j) for j in range(17)]
+    pl.set_initial_paths([protos[b % 17] for b in range(B)])
+    scan = dict(angle_min=-np.pi, angle_max=np.pi, range_min=0.1, range_max=10.0)
+    n_sets, sets = 2, []
+    for s in range(n_sets):
+        k = rng.integers(0, 60, B)
+        st = np.stack([protos[b % 17][k[b], :3] for b in range(B)]) + rng.normal(0, 0.02, (B, 3))
+        sets.append(dict(states=torch.from_numpy(st).pin_memory(), ranges=torch.from_numpy(rng.uniform(2.0, 11.5, (B, R)).astype(np.float32)).pin_memory(),
+                         vel=torch.from_numpy(rng.uniform(-1, 1, (B, 2, R)).astype(np.float32)).pin_memory()))
+    dsets = [{k: v.to(dev) for k, v in d.items()} for d in sets]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lib = _lib.load()
+
+    def step(i, host=False):
+        d = (sets if host else dsets)[i % n_sets]
+        if host:
+            d = {k: v.to(dev, non_blocking=True) for k, v in d.items()}
+        action, _ = pl.forward(d["states"], d["ranges"], scan, scan_velocity=d["vel"])
+        return action.cpu() if host else action
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    l0, tot = lib.nb_launch_count(), 0.0
+    for i in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); step(i); e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    launches = (lib.nb_launch_count() - l0) // args.steps
+    ms = tot / args.steps
+    clocks = sampler.stop()
+    step(0, True); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i, True)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    print(json.dumps(dict(metric="robot control steps/sec (initial path + scan -> points + PAN, batched envs)", value=B / (ms * 1e-3), unit="env-steps/s", n_gpus=1,
+                          steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                          dtype="f64 (path, scan) / fp16 hi-lo tcgen05 (ObsPointNet) / f64 (NRMP)", data="synthetic",
+                          config=dict(workload=f"control: C4 robot, B={B}, T={cfg.T}, K={cfg.K}, scans of R={R} beams -> N={N} points, velocities on", global_batch=B,
+                                      l2="L2 flushed between timed iterations"),
+                          gpu_launches=int(launches), clocks=clocks,
+                          e2e=dict(value=B / (e2e_ms * 1e-3), unit="env-steps/s", h2d_bytes_per_step=int(B * (R * 12 + 24)), d2h_bytes_per_step=int(B * 8), ms_per_step=e2e_ms,
+                                   api="neupan_b200.PlannerBatch.forward on pinned host states + scans -> actions on the host"))))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -504,7 +583,9 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, help="env sub-batches pipelined on internal streams (NB_OPT_OVERLAP)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.workload == "ipath" and args.impl == "ours":
+    if args.workload == "control" and args.impl == "ours":
+        run_control(args)
+    elif args.workload == "ipath" and args.impl == "ours":
         run_ipath(args)
     elif args.workload == "scan" and args.impl == "ours":
         run_scan(args)
