@@ -87,12 +87,6 @@ __device__ __forceinline__ void st16(uint32_t taddr, const uint32_t (&a)[16]) {
                : "memory");
 }
 
-__device__ __forceinline__ void st8(uint32_t taddr, const uint32_t* a) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]),
-               "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7])
-               : "memory");
-}
-
 // every thread writes the same 32-float row (the layer's bias) into its TMEM lane: D := bias
 __device__ __forceinline__ void st_bias32(uint32_t taddr, const float* __restrict__ b) {
   uint32_t v[32];
@@ -560,13 +554,8 @@ __global__ void __launch_bounds__(128, 4) dune_tcp_kernel(const DuneParams prm, 
   // activations (already split) of `slot` -> TMEM, then one thread starts the layer's MMAs (bias product first)
   auto publish = [&](const uint32_t (&hi)[16], const uint32_t (&lo)[16], int slot, int layer) {
     const uint32_t tS = trow + 64 * slot;
-#ifdef NB_TC_ST8
-    tc::st8(tS + 32, hi); tc::st8(tS + 40, hi + 8);
-    tc::st8(tS + 48, lo); tc::st8(tS + 56, lo + 8);
-#else
     tc::st16(tS + 32, hi);
     tc::st16(tS + 48, lo);
-#endif
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     // The issuing warp rotates: warp w of every CTA lives on scheduler w of its SM, so a fixed issuer would put the ~100
