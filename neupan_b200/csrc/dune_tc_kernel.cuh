@@ -1,16 +1,18 @@
-// DUNE kernel, tcgen05 version (Blackwell 5th-gen tensor cores, accumulators in TMEM).
+// DUNE kernels, tcgen05 versions (Blackwell 5th-gen tensor cores, accumulators and A operand in TMEM).
 //
 // Same contract as dune_mma_kernel.cuh / dune_kernel.cuh.  Mapping: CTA = 128 threads = 128 TMEM lanes;
 // thread r owns point r of a 128-point tile for the whole network, so LayerNorm statistics, tanh, ReLU
 // and the distance are thread-local (no shuffles, no fragment bookkeeping).  Per dense layer:
-//   registers --split x = hi + lo (fp16)--> tcgen05.st (A operand, TMEM)         [all threads]
-//   D[128 x 32] = bias (tcgen05.st) + A_lo.B_hi + A_hi.B_lo + A_hi.B_hi           [one thread, tcgen05.mma,
-//                                                               B from shared memory via UMMA descriptors]
-//   tcgen05.commit -> mbarrier -> tcgen05.ld (32 fp32 columns = the thread's row)  [all threads]
+//   registers --split x = hi + lo (fp16)--> tcgen05.st (A operand, TMEM)              [all threads]
+//   D[128 x 32] = ONES.BIASB + A_lo.B_hi + A_hi.B_lo + A_hi.B_hi                       [one elected lane, tcgen05.mma,
+//                                                      B (and ONES) from shared memory via UMMA descriptors]
+//   tcgen05.commit -> mbarrier -> tcgen05.ld (32 fp32 columns = the thread's row)      [all threads]
 // Layouts / descriptors were verified in isolation with tools/tc05_probe.cu.
 //
-// TMEM columns per CTA (64 allocated): D [0,32)  A_hi [32,48)  A_lo [48,64).  D is pre-loaded with the bias row by
-// tcgen05.st (every thread writes the same 32 floats into its lane), all MMAs then accumulate.
+// dune_tcp_kernel (default): two 128-point tiles ("slots") per CTA, 128 TMEM columns = 2 x {D [0,32) | A_hi [32,48) |
+//   A_lo [48,64)}; the epilogue of one slot overlaps the MMAs of the other; packed FP32 / FHFMA epilogue math.
+// dune_tc_kernel (NB_DUNE_TC=1): the first version -- one slot (64 columns), bias row written into D by tcgen05.st,
+//   scalar epilogue math, every layer waits for its MMAs.
 #pragma once
 #include <cuda_fp16.h>
 
