@@ -108,3 +108,40 @@ def test_gather_world_size_2_gloo(total):
     res = sorted(q.get(timeout=120) for _ in procs)
     [p.join(60) for p in procs]
     assert res == [(0, True), (1, True)]
+
+
+def test_scan_and_ipath_struct_layouts_match_header():
+    # nb_scan_config: 4 + 3 + 2 doubles, 2 int32;  nb_ipath_config: 8 int32, 4 doubles
+    assert C.sizeof(_lib.ScanConfig) == 9 * 8 + 2 * 4 and _lib.ScanConfig.down_sample.offset == 72
+    assert C.sizeof(_lib.IpathConfig) == 8 * 4 + 4 * 8 and _lib.IpathConfig.step_time.offset == 32
+
+
+def test_scan_and_ipath_reject_bad_arguments_before_touching_the_device(lib):
+    cfg = _lib.ScanConfig(angle_min=-1.0, angle_max=1.0, range_min=0.1, range_max=5.0, down_sample=1)
+    one = C.c_void_p(8)  # never dereferenced: validation comes first
+    assert lib.nb_scan_to_points(1, 16, None, None, one, C.byref(cfg), 16, one, None, one, None) == _lib.NB_ERR_INVALID
+    assert lib.nb_scan_to_points(1, 0, one, None, one, C.byref(cfg), 16, one, None, one, None) == _lib.NB_ERR_INVALID
+    cfg.down_sample = 0
+    assert lib.nb_scan_to_points(1, 16, one, None, one, C.byref(cfg), 16, one, None, one, None) == _lib.NB_ERR_INVALID
+    assert b"down_sample" in lib.nb_last_error()
+    cfg.down_sample = 1
+    assert lib.nb_scan_to_points(1, 60000, one, None, one, C.byref(cfg), 16, one, None, one, None) == _lib.NB_ERR_CAPACITY
+    h = C.c_void_p()
+    ic = _lib.IpathConfig(receding=0, kinematics=0, max_envs=1, step_time=0.1)
+    assert lib.nb_ipath_create(C.byref(ic), C.byref(h)) == _lib.NB_ERR_INVALID
+    ic.receding, ic.kinematics = 10, 1  # acker without a wheelbase
+    assert lib.nb_ipath_create(C.byref(ic), C.byref(h)) == _lib.NB_ERR_INVALID
+    assert lib.nb_ipath_step(None, 1, one, one, 4.0, one, one, one, one, one, None) == _lib.NB_ERR_INVALID
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")
+def test_scan_and_ipath_have_no_cpu_fallback(lib):
+    from neupan_b200 import InitialPathBatch, scan_to_points
+
+    h = C.c_void_p()
+    ic = _lib.IpathConfig(receding=10, kinematics=0, max_envs=1, step_time=0.1, ind_range=10, arrive_index_threshold=1)
+    assert lib.nb_ipath_create(C.byref(ic), C.byref(h)) == _lib.NB_ERR_NO_DEVICE
+    with pytest.raises(RuntimeError):
+        scan_to_points(torch.zeros(1, 3), torch.ones(1, 8), dict(angle_min=-1, angle_max=1, range_min=0.1, range_max=5))
+    with pytest.raises(RuntimeError):
+        InitialPathBatch(10, 0.1, "diff")
