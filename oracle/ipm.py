@@ -34,7 +34,9 @@ def condense(p: NrmpProblem):
     return s0, F
 
 
-def solve_ipm(p: NrmpProblem, max_iter: int = 60, tol: float = 1e-11, verbose: bool = False):
+def assemble(p: NrmpProblem):
+    """The condensed program in matrix form:  min 0.5 x'Px + c'x + (rho/2) sum_k max(0, J_k x + k_k)^2  s.t.  Ab x <= bb,
+    x = (U time-major (2T), D (T)).  Returns a dict with P, c, Ab, bb, J, k, rho, n, nU, nD, s0, F, T, M."""
     T, M = p.T, p.M
     nU = 2 * T
     nD = T if M > 0 else 0
@@ -90,6 +92,14 @@ def solve_ipm(p: NrmpProblem, max_iter: int = 60, tol: float = 1e-11, verbose: b
             J[t * M + m, nU + t] = 1.0
             k[t * M + m] = p.fb[t, m] - p.fa[t, m] @ s0[t][0:2]
     rho = p.ro_obs
+
+    return dict(P=P, c=c, Ab=Ab, bb=bb, J=J, k=k, rho=rho, n=n, nU=nU, nD=nD, s0=s0, F=F, T=T, M=M)
+
+
+def solve_ipm(p: NrmpProblem, max_iter: int = 60, tol: float = 1e-11, verbose: bool = False):
+    m_ = assemble(p)
+    P, c, Ab, bb, J, k, rho = m_["P"], m_["c"], m_["Ab"], m_["bb"], m_["J"], m_["k"], m_["rho"]
+    n, nU, nD, s0, F, T, M = m_["n"], m_["nU"], m_["nD"], m_["s0"], m_["F"], m_["T"], m_["M"]
 
     # strictly feasible start
     x = np.zeros(n)
