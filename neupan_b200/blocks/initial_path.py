@@ -119,9 +119,11 @@ class CurveGenerator:
 
 def _make_generator():
     try:
-        from gctl import curve_generator  # the reference's dependency, when present
+        import gctl  # the reference's dependency, when present
 
-        return curve_generator()
+        if getattr(gctl, "__file__", None) is None:  # an in-memory placeholder (e.g. the test loader's stub), not the package
+            raise ImportError("gctl is not installed")
+        return gctl.curve_generator()
     except Exception:
         return CurveGenerator()
 
@@ -197,7 +199,10 @@ class InitialPath:
     def cal_average_interval(self, path):
         if len(path) < 2:
             return 0
-        return sum(math.hypot(float(q[0] - p[0]), float(q[1] - p[1])) for p, q in zip(path, path[1:])) / (len(path) - 1)
+        dist_sum = 0.0  # sequential additions like initial_path.py:157-162 (the builtin sum() is compensated and can differ in the
+        for p, q in zip(path, path[1:]):  # last bit, which flips `ref_speed * dt >= interval` when the spacing equals ref_speed * dt)
+            dist_sum += math.hypot(float(np.asarray(q[0] - p[0]).reshape(-1)[0]), float(np.asarray(q[1] - p[1]).reshape(-1)[0]))
+        return dist_sum / (len(path) - 1)
 
     def closest_point(self, state, threshold=0.1, ind_range=10):
         min_dis = inf

@@ -65,6 +65,28 @@ def test_the_reference_rewrites_its_path_and_the_oracle_follows():
     assert np.array_equal(before[:, [0, 1, 3]], after[:, [0, 1, 3]]) and not np.array_equal(before[:, 2], after[:, 2])
 
 
+@pytest.mark.parametrize("name", list(SC))
+def test_host_initial_path_of_the_facade_reproduces_the_reference(name):
+    """neupan_b200.blocks.InitialPath (the single-robot host class behind the `neupan` facade) replayed on the recorded inputs:
+    bit for bit what the reference class returned, including the path it leaves behind."""
+    from neupan_b200.blocks.initial_path import InitialPath
+
+    kin, L, loop, step, split, curve, n = SC[name]
+    rb = type("Robot", (), dict(kinematics=kin, L=L, max_speed=np.array([8.0, 1.0])))()
+    ip = InitialPath(T, DT, REF_SPEED, rb, loop=loop)
+    ip.set_initial_path([p.copy() for p in mgi.make_path(n, step, split, curve)])
+    g = _gold(name)
+    for k in range(len(g["arrived"])):
+        state = g["states"][k].reshape(3, 1)
+        arrived = ip.check_arrive(state)
+        assert arrived == bool(g["arrived"][k]) and ip.point_index == g["point_index"][k] and ip.curve_index == g["curve_index"][k]
+        if arrived:
+            break
+        nom_s, nom_u, ref_s, ref_us = ip.generate_nom_ref_state(state, g["vel"][k], REF_SPEED)
+        assert np.array_equal(nom_s, g["nom_s"][k]) and np.array_equal(ref_s, g["ref_s"][k]) and np.array_equal(np.asarray(ref_us), g["ref_us"][k])
+    assert np.array_equal(np.hstack([p for c in ip.curve_list for p in c]).T, g["final_path"])
+
+
 def test_pack_paths_layout():
     paths = [mgi.make_path(12, 0.4, 5, 0.0), mgi.make_path(7, 0.4, None, 0.0)]
     pts, cb, eb = oip.pack_paths(paths)
