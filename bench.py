@@ -181,7 +181,7 @@ def run_ours(args):
     dsets = [{k: (None if v is None else v.to(dev)) for k, v in s.items()} for s in sets]
     hsets = [{k: (None if v is None else v.pin_memory()) for k, v in s.items()} for s in sets]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    pan = make_pan(cfg, K=K, iter_threshold=0.0, max_envs=B, overlap=args.overlap, dune_kernel=args.dune_kernel)
+    pan = make_pan(cfg, K=K, iter_threshold=args.iter_threshold, max_envs=B, overlap=args.overlap, dune_kernel=args.dune_kernel)
     lib = _lib.load()
     per_env = 3 * (T + 1) + 2 * T + T + 1
     packed = torch.empty(B, per_env, device=dev)
@@ -303,7 +303,7 @@ def run_ours(args):
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32-accurate fp16 hi/lo split on tcgen05 tensor cores (ObsPointNet) / f64 (NRMP interior point)",
                     data="synthetic",
-                    config=dict(workload=f"{args.workload} {cfg.name}: B={B}/GPU T={T} N={N} K={K} M={cfg.M} dyn={cfg.dynamic}", global_batch=world * B,
+                    config=dict(workload=f"{args.workload} {cfg.name}: B={B}/GPU T={T} N={N} K={K} M={cfg.M} dyn={cfg.dynamic}" + (f" iter_threshold={args.iter_threshold} (early stop active)" if args.iter_threshold > 0 else ""), global_batch=world * B,
                                 parallelism=f"env-sharded x{world}, one all_gather of {per_env} floats/env per step",
                                 l2="2 rotating input sets + 256 MiB flush between timed steps", scene="annulus (SURVEY 8d)"),
                     e2e=dict(value=world * B / (float(e2e_ms.item()) * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
@@ -580,6 +580,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="override B per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--dune-kernel", type=int, default=2, help="NB_OPT_DUNE_KERNEL: 0 fp32 ffma, 1 mma.sync, 2 tcgen05")
+    ap.add_argument("--iter-threshold", type=float, default=0.0, help="PAN stop criterion (pan.py:243); 0 forces exactly K iterations (the headline), the reference default is 0.1")
     ap.add_argument("--overlap", type=int, default=1, help="env sub-batches pipelined on internal streams (NB_OPT_OVERLAP)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
