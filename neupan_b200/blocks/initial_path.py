@@ -4,8 +4,9 @@ Mirrors the interface of neupan/blocks/initial_path.py:28-498 (same constructor 
 and methods, same nominal / reference construction in ``generate_nom_ref_state``), host-side numpy.
 The reference delegates curve generation to the third-party ``gctl.curve_generator`` (pinned
 gctl==1.2, absent here); this module uses gctl when it is importable and otherwise its own generator:
-``line`` (points every ``interval`` along each segment) and ``dubins`` (shortest of the six Dubins
-words at ``min_radius``).  ``reeds`` needs gctl.  Point placement of the built-in generator is not
+``line`` (points every ``interval`` along each segment), ``dubins`` (shortest of the six Dubins
+words at ``min_radius``) and ``reeds`` (shortest Reeds-Shepp word, ``reeds_shepp.py``; backward
+segments carry gear -1).  Point placement of the built-in generator is not
 verified against gctl (it could not be run here) -- only the spacing / heading conventions the
 reference relies on are kept: points are (4,1) columns [x, y, theta, gear].
 """
@@ -34,14 +35,20 @@ class CurveGenerator:
                 seg = self._line(a, b, step_size)
             elif curve_style == "dubins":
                 seg = self._dubins(a, b, step_size, max(min_radius, 1e-6))
+            elif curve_style == "reeds":
+                from .reeds_shepp import sample_path
+
+                seg = sample_path(a, b, step_size, max(min_radius, 1e-6))
             else:
-                raise NotImplementedError(f"curve_style '{curve_style}' needs the gctl package (not installed)")
+                raise ValueError(f"curve_style '{curve_style}' is not one of line, dubins, reeds")
             if pts and seg:
                 seg = seg[1:]  # the joint waypoint is already there
             pts += seg
         out = []
-        for x, y, th in pts:
-            col = np.array([[x], [y], [th], [1.0]]) if include_gear else np.array([[x], [y], [th]])
+        for pt in pts:
+            x, y, th = pt[0], pt[1], pt[2]
+            gear = pt[3] if len(pt) > 3 else 1.0  # only Reeds-Shepp curves drive backwards
+            col = np.array([[x], [y], [th], [gear]]) if include_gear else np.array([[x], [y], [th]])
             out.append(col)
         return out
 

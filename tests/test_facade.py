@@ -37,8 +37,8 @@ def test_curve_generator_line_and_dubins():
     # curvature bound: heading change per arc length <= 1/r
     dth = [abs((b[2, 0] - a[2, 0] + np.pi) % (2 * np.pi) - np.pi) for a, b in zip(dub, dub[1:])]
     assert max(d / s for d, s in zip(dth, steps) if s > 1e-9) <= 1.01 / 3.0  # chord < arc by < 1 %
-    with pytest.raises(NotImplementedError):
-        cg.generate_curve("reeds", [np.c_[[0, 0, 0.0]], np.c_[[1, 1, 0.0]]], 0.1, 1.0, True)
+    reeds = cg.generate_curve("reeds", [np.c_[[0, 0, 0.0]], np.c_[[1, 1, 0.0]]], 0.1, 1.0, True)
+    assert np.allclose(reeds[-1][:3, 0], [1, 1, 0.0], atol=1e-6)
 
 
 def test_initial_path_nominal_and_reference():
@@ -135,3 +135,43 @@ def test_facade_step_matches_oracle(tmp_path):
     S, U, D = o.forward(ns.astype(np.float32), nu.astype(np.float32), rs.astype(np.float32), rus.astype(np.float32), pts.astype(np.float32), None)
     assert rel_err(info["vel_tensor"].numpy(), U) < 1e-4 and rel_err(info["state_tensor"].numpy(), S) < 1e-4
     assert np.allclose(action[:, 0], U[:, 0], atol=1e-4)
+
+
+def test_reeds_shepp_curves():
+    """curve_style 'reeds' (host generator, neupan_b200/blocks/reeds_shepp.py): every candidate word is verified by
+    integration; shortest verified word; symmetric under exchanging start and goal; never longer than the Dubins curve."""
+    import math
+
+    from neupan_b200.blocks import reeds_shepp as rs
+    from neupan_b200.blocks.initial_path import CurveGenerator
+
+    rng = np.random.default_rng(1)
+    cg = CurveGenerator()
+    for _ in range(300):
+        x, y, phi = rng.uniform(-6, 6), rng.uniform(-6, 6), rng.uniform(-math.pi, math.pi)
+        for types, lengths in rs._candidates(x, y, phi):  # the closed forms are right: each generated word reaches the goal
+            ex, ey, eh, _ = rs.integrate(types, lengths)
+            assert math.hypot(ex - x, ey - y) < 1e-6 and abs(rs._mod2pi(eh - phi)) < 1e-6
+        types, lengths, total = rs.shortest_word(x, y, phi)
+        c, s = math.cos(phi), math.sin(phi)
+        _, _, back = rs.shortest_word(-(c * x + s * y), -(-s * x + c * y), -phi)
+        assert abs(total - back) < 1e-6
+        r = 1.5
+        a, b = np.array([0.0, 0.0, 0.0]), np.array([r * x, r * y, phi])
+        dub = cg._dubins(a, b, 0.2, r)
+        dub_len = sum(math.hypot(q[0] - p[0], q[1] - p[1]) for p, q in zip(dub, dub[1:]))
+        assert total * r <= dub_len + 0.05  # chord-sampled Dubins length is a slight underestimate of its arc length
+    # straight behind: drive backwards
+    types, lengths, total = rs.shortest_word(-3.0, 0.0, 0.0)
+    assert abs(total - 3.0) < 1e-9
+    path = cg.generate_curve("reeds", [np.array([0.0, 0.0, 0.0]), np.array([-3.0, 0.0, 0.0])], 0.25, 1.0, True)
+    assert all(p.shape == (4, 1) for p in path) and all(p[3, 0] == -1.0 for p in path[1:])
+    assert abs(path[-1][0, 0] + 3.0) < 1e-9 and abs(path[-1][1, 0]) < 1e-9
+    # a parking-like manoeuvre: the path changes gear, reaches the goal, and its points are at most one step apart
+    path = cg.generate_curve("reeds", [np.array([0.0, 0.0, 0.0]), np.array([0.5, 2.0, math.pi])], 0.2, 1.0, True)
+    gears = [p[3, 0] for p in path]
+    assert 1.0 in gears and -1.0 in gears
+    assert math.hypot(path[-1][0, 0] - 0.5, path[-1][1, 0] - 2.0) < 1e-6 and abs(rs._mod2pi(path[-1][2, 0] - math.pi)) < 1e-6
+    assert max(math.hypot(q[0, 0] - p[0, 0], q[1, 0] - p[1, 0]) for p, q in zip(path, path[1:])) <= 0.2 + 1e-9
+    with pytest.raises(ValueError):
+        cg.generate_curve("spline", [np.zeros(3), np.ones(3)], 0.1, 1.0, True)
