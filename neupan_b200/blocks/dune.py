@@ -9,6 +9,8 @@ from __future__ import annotations
 from math import inf
 from typing import Optional
 
+import os
+
 import numpy as np
 import torch
 
@@ -52,7 +54,24 @@ class DUNE(torch.nn.Module):
         self.model.eval()
 
     def train_dune(self, train_kwargs):
-        raise NotImplementedError("DUNE training (neupan/blocks/dune_train.py) is outside the B200 hot path (SURVEY.md 8f #4)")
+        """dune.py:173-182: trains ``self.model`` and saves ``model/<model_name>/model_<epoch>.pth`` next to the running script.
+        The native PAN handle keeps the weights it was created with: construct the planner from the new checkpoint to use it."""
+        import sys
+
+        from .dune_train import DUNETrain
+
+        train_kwargs = dict(train_kwargs or {})
+        model_name = train_kwargs.pop("model_name", getattr(self.robot, "name", "robot"))
+        train_kwargs.pop("direct_train", None)
+        base = train_kwargs.pop("checkpoint_dir", os.path.join(sys.path[0], "model"))
+        path, k = os.path.join(base, model_name), 0
+        while os.path.exists(path):  # util.repeat_mk_dirs: append a counter instead of overwriting
+            k += 1
+            path = os.path.join(base, f"{model_name}_{k}")
+        self.train_model = DUNETrain(self.model, self.G, self.h, path)
+        self.full_model_name = self.train_model.start(**train_kwargs)
+        print("Complete Training. The model is saved in " + str(self.full_model_name))
+        return self.full_model_name
 
     @property
     def points(self):
