@@ -79,87 +79,222 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU path (the oracle port of the reference: oracle/pan.py) -- cpu_baseline and --impl reference
 # --------------------------------------------------------------------------------------------
+def host_cores() -> int:
+    """Cores this process may actually run on (cgroup / affinity aware), not the machine's total."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def _cpu_worker(args):
-    cname, env_ids, K = args
+    """One task = a list of environments run one after the other through the CPU oracle (oracle/pan.py).
+    A failing environment is counted, never fatal (round 1 lost the whole arm to one Cholesky failure)."""
+    cname, env_ids, K, thr = args
     import torch
 
     torch.set_num_threads(1)
     from helpers import CONFIGS, make_inputs, oracle_factory
 
     cfg = CONFIGS[cname]
-    mk = oracle_factory(cfg, K=K)
-    t0 = time.perf_counter()
+    mk = oracle_factory(cfg, K=K, iter_threshold=thr)
+    out = dict(envs=0, failed=0, fallbacks=0, t_dune=0.0, t_nrmp=0.0, iters=0, wall=0.0, cpu=0.0)
+    t0, c0 = time.perf_counter(), time.process_time()
     for e in env_ids:
         inp = make_inputs(cfg, B=1, env_offset=e)
         pan = mk()
         vel = None if inp["velocities"] is None else inp["velocities"][0]
-        pan.forward(inp["nom_s"][0], inp["nom_u"][0], inp["ref_s"][0], inp["ref_us"][0], inp["points"][0], vel)
-    return time.perf_counter() - t0
+        try:
+            pan.forward(inp["nom_s"][0], inp["nom_u"][0], inp["ref_s"][0], inp["ref_us"][0], inp["points"][0], vel)
+            out["envs"] += 1
+        except Exception:  # noqa: BLE001 -- reported as a count
+            out["failed"] += 1
+        out["fallbacks"] += pan.fallbacks
+        out["t_dune"] += pan.t_dune
+        out["t_nrmp"] += pan.t_nrmp
+        out["iters"] += pan.iters_run
+    out["wall"], out["cpu"] = time.perf_counter() - t0, time.process_time() - c0
+    return out
 
 
 class CpuPool:
-    """Persistent worker processes (one per core, one thread each); start-up and imports are paid
+    """Persistent worker processes (one per usable core, one thread each); start-up and imports are paid
     once in a warm-up task so that the timed region only contains oracle work."""
 
-    def __init__(self, cname: str, K: int, procs: int):
+    def __init__(self, cname: str, K: int, procs: int, iter_threshold: float = 0.0):
         import multiprocessing as mp
 
         for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
             os.environ[var] = "1"  # inherited by the spawned workers
-        self.cname, self.K, self.procs = cname, K, procs
+        self.cname, self.K, self.procs, self.thr = cname, K, procs, iter_threshold
         self.pool = mp.get_context("spawn").Pool(procs)
-        self.pool.map(_cpu_worker, [(cname, [10 ** 6 + i], 1) for i in range(procs)])  # warm-up: imports, page-in
+        # warm-up: imports, page-in, one full-K environment per worker (first-call costs of torch / scipy)
+        self.pool.map(_cpu_worker, [(cname, [10 ** 6 + i], K, iter_threshold) for i in range(procs)], chunksize=1)
 
-    def rate(self, n_envs: int, first_env: int = 0):
-        """env-steps/s over n_envs environments spread over the workers."""
+    def run(self, n_envs: int, first_env: int = 0) -> dict:
+        """n_envs environments spread round-robin over the workers; returns wall-clock rate and the split."""
         chunks = [list(range(first_env + i, first_env + n_envs, self.procs)) for i in range(self.procs)]
         chunks = [c for c in chunks if c]
         t0 = time.perf_counter()
-        self.pool.map(_cpu_worker, [(self.cname, c, self.K) for c in chunks], chunksize=1)
+        res = self.pool.map(_cpu_worker, [(self.cname, c, self.K, self.thr) for c in chunks], chunksize=1)
         wall = time.perf_counter() - t0
-        return n_envs / wall, wall
+        tot = {k: sum(r[k] for r in res) for k in res[0]}
+        done = max(1, tot["envs"])
+        return dict(rate=tot["envs"] / wall, wall=wall, envs=tot["envs"], failed=tot["failed"], fallbacks=tot["fallbacks"],
+                    dune_ms_per_env=1e3 * tot["t_dune"] / done, nrmp_ms_per_env=1e3 * tot["t_nrmp"] / done, iters_per_env=tot["iters"] / done,
+                    # throughput the same work would reach if every worker had a core to itself all the time: a wall-clock
+                    # rate far below it means the host was shared / oversubscribed during the sample
+                    rate_from_cpu_time=len(chunks) * tot["envs"] / max(tot["cpu"], 1e-9), slowest_worker_s=max(r["wall"] for r in res))
 
     def close(self):
         self.pool.close()
         self.pool.join()
 
 
+def cpu_sample(cname: str, K: int, iter_threshold: float, rounds: int, envs_per_worker: int, first_env: int = 0):
+    """`rounds` back-to-back samples of envs_per_worker x cores environments; returns (summary dict, per-round list)."""
+    cores = host_cores()
+    pool = CpuPool(cname, K, cores, iter_threshold)
+    per_round = cores * envs_per_worker
+    runs = [pool.run(per_round, first_env=first_env + i * per_round) for i in range(rounds)]
+    pool.close()
+    rates = [r["rate"] for r in runs]
+    walls = [r["wall"] for r in runs]
+    envs = sum(r["envs"] for r in runs)
+    mean = lambda key: float(sum(r[key] * r["envs"] for r in runs) / max(1, envs))
+    summary = dict(value=envs / sum(walls), cores=cores, rounds=rounds, envs_per_round=per_round, envs=envs,
+                   failed_envs=sum(r["failed"] for r in runs), highs_fallback_solves=sum(r["fallbacks"] for r in runs),
+                   rate_per_round=rates, spread=(max(rates) - min(rates)) / max(rates) if rates else None, wall_s=sum(walls),
+                   dune_ms_per_env=mean("dune_ms_per_env"), nrmp_ms_per_env=mean("nrmp_ms_per_env"), pan_iterations_per_env=mean("iters_per_env"),
+                   env_steps_per_s_per_core=envs / sum(walls) / cores, rate_from_cpu_time=float(np.mean([r["rate_from_cpu_time"] for r in runs])))
+    return summary, runs
+
+
+CPU_WHAT = ("oracle/pan.py: the reference's torch-CPU DUNE code restated (pinned bit-for-bit to the reference) + float64 interior point "
+            "solve of the reference's program in place of cvxpylayers/ECOS (not installable here); one process per core, one thread each")
+
+
 def run_reference(args):
+    """--impl reference: the CPU path alone on all usable host cores.  A step = 8 environments per core (one full pass of the
+    hot path, K PAN iterations, per environment); at most 4 timed steps so that the driver's --steps 20 ends within minutes."""
     from helpers import CONFIGS
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = CONFIGS[args.workload]
-    cores = os.cpu_count() or 1
-    per_step = 2 * cores
-    pool = CpuPool(args.workload, cfg.K, cores)
-    for w in range(min(args.warmup, 1)):
-        pool.rate(cores, first_env=5 * 10 ** 5)
-    times = []
-    for i in range(max(1, min(args.steps, 4))):
-        rate, wall = pool.rate(per_step, first_env=i * per_step)
-        times.append(wall)
-    pool.close()
-    ms = 1e3 * float(np.mean(times))
-    value = per_step / (ms / 1e3)
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=len(times), warmup=min(args.warmup, 1), ms_per_step=ms, higher_is_better=True,
+    steps = max(1, min(args.steps, 4))
+    summ, runs = cpu_sample(args.workload, cfg.K, args.iter_threshold, steps, 8)
+    ms = 1e3 * summ["wall_s"] / steps
+    value = summ["value"]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=max(args.gpus, world), steps=steps, warmup=1, ms_per_step=ms, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32 (MLP) / f64 (QP)", data="synthetic", impl="reference",
-                config=dict(workload=f"{args.workload} {cfg.name}: T={cfg.T} N={cfg.N} K={cfg.K} M={cfg.M}", envs_per_step=per_step),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
-                                  sample=f"{per_step} envs/step x {len(times)} steps of {args.workload} on {cores} worker processes; oracle/pan.py (reference DUNE code restated + float64 IPM for the ECOS solve; cvxpylayers/ECOS not installable)"),
-                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                config=dict(workload=f"{args.workload} {cfg.name}: T={cfg.T} N={cfg.N} K={cfg.K} M={cfg.M} dyn={cfg.dynamic}", envs_per_step=summ["envs_per_round"],
+                            note="CPU arm: throughput does not depend on the GPU count; rank 0 alone runs it"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=summ["cores"], kind="port",
+                                  sample=f"{summ['envs_per_round']} envs/step x {steps} steps of {args.workload} (8 envs per worker process, {summ['cores']} processes, warm-up = 1 env per worker); {CPU_WHAT}",
+                                  **{k: summ[k] for k in ("failed_envs", "highs_fallback_solves", "rate_per_round", "spread", "dune_ms_per_env", "nrmp_ms_per_env",
+                                                           "pan_iterations_per_env", "env_steps_per_s_per_core", "rate_from_cpu_time")}),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------
+class PanBench:
+    """One workload on this rank's GPU: B_local environments (global batch = sum over ranks), two rotating input
+    sets (distinct environments) + a 256 MiB L2 flush between timed steps.  Every step -- device-resident or from
+    pinned host memory -- goes through neupan_b200.parallel.ShardedPAN (PAN.forward + the one all_gather)."""
+
+    def __init__(self, cname, B_local, env_base, dev, world, total, args, iter_threshold=0.0, flush=None):
+        import torch
+
+        from gpu_helpers import make_pan
+        from helpers import CONFIGS, make_inputs
+        from neupan_b200 import _lib
+        from neupan_b200.parallel import ShardedPAN
+
+        self.torch, self.cfg, self.B, self.dev, self.world, self.total = torch, CONFIGS[cname], B_local, dev, world, total
+        cfg = self.cfg
+        self.n_sets = 2
+        sets = []
+        for s_ in range(self.n_sets):
+            inp = make_inputs(cfg, B=B_local, env_offset=env_base + s_ * total)
+            sets.append({k: (None if v is None else torch.from_numpy(v)) for k, v in inp.items()})
+        self.dsets = [{k: (None if v is None else v.to(dev)) for k, v in s_.items()} for s_ in sets]
+        self.hsets = [{k: (None if v is None else v.pin_memory()) for k, v in s_.items()} for s_ in sets]
+        self.flush = flush if flush is not None else torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+        self.pan = make_pan(cfg, K=cfg.K, iter_threshold=iter_threshold, max_envs=B_local, overlap=args.overlap, dune_kernel=args.dune_kernel)
+        self.sp = ShardedPAN(self.pan, total)
+        self.lib = _lib.load()
+
+    def step(self, i, host=False):
+        d = (self.hsets if host else self.dsets)[i % self.n_sets]
+        return self.sp.step(d["nom_s"], d["nom_u"], d["ref_s"], d["ref_us"], d["points"], d["velocities"])
+
+    def barrier(self):
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce_max(self, x: float) -> float:
+        import torch.distributed as dist
+
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_device(self, steps, warmup):
+        """(ms per step: CUDA events on the launching stream, mean over steps, max over ranks; launches per step)."""
+        torch = self.torch
+        for i in range(warmup):
+            self.flush.zero_()
+            self.step(i)
+        self.barrier()
+        l0 = self.lib.nb_launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        self.barrier()
+        for i in range(steps):
+            self.flush.zero_()  # L2 flush, outside the per-step events
+            ev[i][0].record()
+            self.step(i)
+            ev[i][1].record()
+        self.barrier()
+        launches = (self.lib.nb_launch_count() - l0) // max(1, steps)
+        ms = self.reduce_max(sum(a.elapsed_time(b) for a, b in ev) / steps)
+        return ms, int(launches)
+
+    def time_e2e(self, steps):
+        """Pinned host inputs -> H2D -> PAN -> all_gather -> D2H of the gathered result, wall clock around synchronised steps."""
+        for i in range(2):
+            self.step(i, host=True)
+        self.barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            self.step(i, host=True)  # ends with a stream synchronise (the result is on the host)
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        return self.reduce_max(ms)
+
+    def bytes_per_step(self):
+        cfg, B, T = self.cfg, self.B, self.cfg.T
+        h2d = 4 * B * (2 * 3 * (T + 1) + 2 * T + T + (2 * cfg.N) * (2 if cfg.dynamic else 1))
+        d2h = 4 * self.total * (3 * (T + 1) + 2 * T + T + 1)
+        return h2d, d2h
+
+    def close(self):
+        self.pan.close()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from gpu_helpers import make_pan
-    from helpers import CONFIGS, make_inputs
+    from helpers import CONFIGS
     from neupan_b200 import _lib
+    from neupan_b200.parallel import shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -171,75 +306,24 @@ def run_ours(args):
     cfg = CONFIGS[args.workload]
     B = args.envs or cfg.B
     T, N, K = cfg.T, cfg.N, cfg.K
-
-    # rotating input sets (distinct envs) so consecutive steps never see the same data; plus an L2 flush
-    n_sets = 2
-    sets = []
-    for s in range(n_sets):
-        inp = make_inputs(cfg, B=B, env_offset=(rank * n_sets + s) * B)
-        sets.append({k: (None if v is None else torch.from_numpy(v)) for k, v in inp.items()})
-    dsets = [{k: (None if v is None else v.to(dev)) for k, v in s.items()} for s in sets]
-    hsets = [{k: (None if v is None else v.pin_memory()) for k, v in s.items()} for s in sets]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    pan = make_pan(cfg, K=K, iter_threshold=args.iter_threshold, max_envs=B, overlap=args.overlap, dune_kernel=args.dune_kernel)
-    lib = _lib.load()
     per_env = 3 * (T + 1) + 2 * T + T + 1
-    packed = torch.empty(B, per_env, device=dev)
-    gathered = torch.empty(world * B, per_env, device=dev) if world > 1 else None
+    lib = _lib.load()
 
-    def step(i, host=False):
-        d = (hsets if host else dsets)[i % n_sets]
-        S, U, D = pan(d["nom_s"], d["nom_u"], d["ref_s"], d["ref_us"], d["points"], d["velocities"])
-        if host:
-            return S
-        if world > 1:  # the one exchange of the path: gather per-env trajectories
-            torch.cat([S.reshape(B, -1), U.reshape(B, -1), D.reshape(B, -1), pan.min_distance.reshape(B, 1)], 1, out=packed)
-            dist.all_gather_into_tensor(gathered, packed)
-        return S
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(args.warmup):
-        flush.zero_()
-        step(i)
-    barrier()
+    # ---- headline: weak scaling, B environments per GPU, K iterations forced (iter_threshold = 0) ----------------
+    hb = PanBench(args.workload, B, rank * B, dev, world, world * B, args, iter_threshold=args.iter_threshold)
     sampler = ClockSampler(local)
+    for i in range(2):
+        hb.step(i)
+    hb.barrier()
     if rank == 0:
         sampler.start()
-    l0 = lib.nb_launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for i in range(args.steps):
-        flush.zero_()  # L2 flush, outside the per-step events
-        ev[i][0].record()
-        step(i)
-        ev[i][1].record()
-    barrier()
-    launches = (lib.nb_launch_count() - l0) // max(1, args.steps)
-    step_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / args.steps], device=dev)
-    if world > 1:
-        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
-    ms = float(step_ms.item())
+    ms, launches = hb.time_device(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    status_bad = int((pan.status != 0).sum().item())
-
-    # ---- e2e: host tensors through the public API (H2D + compute + D2H per step) ----------------
-    for i in range(2):
-        step(i, host=True)
-    barrier()
-    t0 = time.perf_counter()
-    n_e2e = max(2, min(args.steps, 5))
-    for i in range(n_e2e):
-        step(i, host=True)
-    torch.cuda.synchronize()
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_e2e], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    h2d = 4 * B * (2 * 3 * (T + 1) + 2 * T + T + (2 * N) * (2 if cfg.dynamic else 1))
-    d2h = 4 * B * (3 * (T + 1) + 2 * T + T + 1) + 8 * B
+    status_bad = int((hb.pan.status != 0).sum().item())
+    iters_mean = float(hb.pan.iterations.float().mean().item())
+    e2e_ms = hb.time_e2e(max(2, min(args.steps, 5)))
+    h2d, d2h = hb.bytes_per_step()
+    pan, flush, dsets = hb.pan, hb.flush, hb.dsets
 
     # ---- roofline of the dominant kernel (DUNE), CUDA events around back-to-back launches ----------
     roof = None
@@ -281,22 +365,49 @@ def run_ours(args):
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.workload)
         roof = dict(bound="tensor", achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"], traffic=traffic,
-                    kernel=kname, kernel_ms=dune_ms, share_of_step=K * dune_ms / ms, peak_source=pk["which"],
+                    kernel=kname, kernel_ms=dune_ms, share_of_step=iters_mean * dune_ms / ms, peak_source=pk["which"],
                     algorithmic_flops_per_launch=flops, tensor_executed_tflops=exec_flops / (dune_ms * 1e-3) / 1e12,
                     algorithmic_bytes_per_launch=alg_bytes, hbm_gbs_if_bytes_only=alg_bytes / (dune_ms * 1e-3) / 1e9, hbm_peak_gbs=pk["hbm_gbs"],
                     note="compute-bound path (SURVEY 8d): HBM < 1% utilised; the GEMMs are 32-wide slices between per-point LayerNorm/tanh, "
                          "so the kernel is bound by instruction issue and the MUFU pipe (2 MUFU per tanh), not by the tensor pipe -- DESIGN.md 3.1")
+    hb.close()
+    del hb, pan, dsets
+
+    # ---- what BASELINE.json asks for beside the headline --------------------------------------
+    def side(cname, total, thr=0.0, steps=5, warmup=3, e2e=False):
+        """ms/step and env-steps/s of `total` environments of config cname split over all ranks (strong split when world > 1)."""
+        lo, hi = shard_range(total, rank, world)
+        sb = PanBench(cname, hi - lo, lo, dev, world, total, args, iter_threshold=thr, flush=flush)
+        m, l = sb.time_device(steps, warmup)
+        out = dict(workload=f"{cname} {sb.cfg.name}", global_batch=total, envs_per_gpu=[shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world)],
+                   T=sb.cfg.T, N=sb.cfg.N, K=sb.cfg.K, iter_threshold=thr, ms_per_step=m, env_steps_per_s=total / (m * 1e-3), gpu_launches=l,
+                   pan_iterations_mean=sb.reduce_max(float(sb.pan.iterations.float().mean().item())),
+                   envs_with_solver_status=int(sb.reduce_max(float((sb.pan.status != 0).sum().item()))))
+        if e2e:
+            em = sb.time_e2e(3)
+            out["e2e_ms_per_step"], out["e2e_env_steps_per_s"] = em, total / (em * 1e-3)
+        sb.close()
+        return out
+
+    extra = {}
+    if not args.no_sides and args.workload == "C4" and not args.envs:
+        if world == 1:
+            extra["configs"] = {c: side(c, CONFIGS[c].B, e2e=True) for c in ("C1", "C2", "C3", "C5")}
+        else:
+            # BASELINE.json configs 4 and 5 as written: the GLOBAL batch split over the GPUs (strong scaling)
+            extra["strong"] = {"C4": side("C4", CONFIGS["C4"].B, e2e=True), "C5": side("C5", CONFIGS["C5"].B, e2e=True)}
+        # the reference's default stop criterion (pan.py:52,243): environments leave the loop once the duals settle
+        extra["iter_threshold_0.1"] = side("C4", world * B, thr=0.1)
 
     # ---- cpu baseline (rank 0, N = 1 only), bounded sample ------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        pool = CpuPool(args.workload, K, cores)
-        n = 2 * cores
-        rate, wall = pool.rate(n)
-        pool.close()
-        cpu = dict(value=rate, unit=UNIT, cores=cores, kind="port",
-                   sample=f"{n} envs of {args.workload} (K={K}) over {cores} worker processes (1 thread each), {wall:.1f} s wall; oracle/pan.py")
+        summ, _ = cpu_sample(args.workload, K, args.iter_threshold, rounds=3, envs_per_worker=4)
+        cpu = dict(value=summ["value"], unit=UNIT, cores=summ["cores"], kind="port",
+                   sample=f"3 rounds x {summ['envs_per_round']} envs of {args.workload} (K={K}; 4 envs per worker process, {summ['cores']} processes, 1 thread each, "
+                          f"warm-up = 1 env per worker), {summ['wall_s']:.1f} s wall; {CPU_WHAT}",
+                   **{k: summ[k] for k in ("failed_envs", "highs_fallback_solves", "rate_per_round", "spread", "dune_ms_per_env", "nrmp_ms_per_env",
+                                            "pan_iterations_per_env", "env_steps_per_s_per_core", "rate_from_cpu_time")})
 
     if rank == 0:
         value = world * B / (ms * 1e-3)
@@ -304,12 +415,12 @@ def run_ours(args):
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32-accurate fp16 hi/lo split on tcgen05 tensor cores (ObsPointNet) / f64 (NRMP interior point)",
                     data="synthetic",
                     config=dict(workload=f"{args.workload} {cfg.name}: B={B}/GPU T={T} N={N} K={K} M={cfg.M} dyn={cfg.dynamic}" + (f" iter_threshold={args.iter_threshold} (early stop active)" if args.iter_threshold > 0 else ""), global_batch=world * B,
-                                parallelism=f"env-sharded x{world}, one all_gather of {per_env} floats/env per step",
+                                parallelism=f"env-sharded x{world}, one all_gather of {per_env} floats/env per step (inside the timed region, device-resident and e2e)",
                                 l2="2 rotating input sets + 256 MiB flush between timed steps", scene="annulus (SURVEY 8d)"),
-                    e2e=dict(value=world * B / (float(e2e_ms.item()) * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             ms_per_step=float(e2e_ms.item()), api="neupan_b200.PAN.forward on pinned host tensors -> nb_pan_forward_host"),
+                    e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             ms_per_step=e2e_ms, api="neupan_b200.parallel.ShardedPAN.step on pinned host tensors: H2D -> PAN.forward (nb_pan_forward) -> all_gather -> D2H of the gathered trajectories"),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu, envs_with_solver_status=status_bad,
-                    control_steps_per_s=world / (ms * 1e-3))
+                    pan_iterations_mean=iters_mean, control_steps_per_s=world / (ms * 1e-3), **extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -579,6 +690,7 @@ def main():
     ap.add_argument("--workload", default="C4")
     ap.add_argument("--envs", type=int, default=0, help="override B per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sides", action="store_true", help="skip the side measurements (other BASELINE configs / strong split / iter_threshold=0.1)")
     ap.add_argument("--dune-kernel", type=int, default=2, help="NB_OPT_DUNE_KERNEL: 0 fp32 ffma, 1 mma.sync, 2 tcgen05")
     ap.add_argument("--iter-threshold", type=float, default=0.0, help="PAN stop criterion (pan.py:243); 0 forces exactly K iterations (the headline), the reference default is 0.1")
     ap.add_argument("--overlap", type=int, default=1, help="env sub-batches pipelined on internal streams (NB_OPT_OVERLAP)")

@@ -45,3 +45,44 @@ def gather_results(packed: torch.Tensor, total_envs: int, group=None) -> torch.T
     if all(hi - lo == longest for lo, hi in sizes):
         return out
     return torch.cat([out[r * longest: r * longest + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], dim=0)
+
+
+class ShardedPAN:
+    """One control step of `total_envs` environments over all ranks of a process group: every rank runs the PAN
+    hot path on its contiguous block (shard_range) and the packed results are exchanged with one all_gather --
+    the only collective of the path.  Inputs are this rank's block, either CUDA tensors
+    (device-resident step) or pinned host tensors (end-to-end step: H2D copies, compute, gather, and a D2H copy of
+    the gathered result, all inside this call).
+
+        sp = ShardedPAN(pan, total_envs)
+        packed = sp.step(nom_s, nom_u, ref_s, ref_us, points, velocities)   # (total_envs, 64) for T = 10
+        S, U, D, min_distance = unpack_results(packed, pan.T)
+    """
+
+    def __init__(self, pan, total_envs: int, group=None):
+        self.pan, self.total, self.group = pan, int(total_envs), group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.lo, self.hi = shard_range(self.total, self.rank, self.world)
+        self._host_out = None
+
+    def step(self, nom_s, nom_u, ref_s, ref_us, points=None, velocities=None, num_points=None) -> torch.Tensor:
+        pan = self.pan
+        host = nom_s.device.type != "cuda"
+        if host:
+            up = lambda t: None if t is None else t.to(pan.device, non_blocking=True)
+            nom_s, nom_u, ref_s, ref_us, points, velocities, num_points = (up(t) for t in (nom_s, nom_u, ref_s, ref_us, points, velocities, num_points))
+        S, U, D = pan(nom_s, nom_u, ref_s, ref_us, points, velocities, num_points)
+        B = S.shape[0]
+        md = pan.min_distance if torch.is_tensor(pan.min_distance) else torch.full((B,), float("inf"), device=S.device)
+        if D is None:
+            D = torch.zeros((B, 1, pan.T), device=S.device)
+        packed = pack_results(S, U, D, md)
+        out = gather_results(packed, self.total, self.group) if self.world > 1 else packed
+        if not host:
+            return out
+        if self._host_out is None or self._host_out.shape != out.shape:
+            self._host_out = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        self._host_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(pan.device).synchronize()
+        return self._host_out

@@ -96,7 +96,33 @@ def assemble(p: NrmpProblem):
     return dict(P=P, c=c, Ab=Ab, bb=bb, J=J, k=k, rho=rho, n=n, nU=nU, nD=nD, s0=s0, F=F, T=T, M=M)
 
 
-def solve_ipm(p: NrmpProblem, max_iter: int = 60, tol: float = 1e-11, verbose: bool = False):
+class IpmFailure(RuntimeError):
+    """The interior point iteration could neither converge nor hand back an acceptable iterate."""
+
+
+def _guarded_cholesky(H):
+    """Cholesky with a growing diagonal shift.  Near the end of the iteration the barrier weights
+    W = z/s of the active rows reach 1e12+ and H loses definiteness to rounding; a shift of a few
+    ulps of its largest diagonal entry restores it without moving the Newton step measurably."""
+    try:
+        return np.linalg.cholesky(H), 0.0
+    except np.linalg.LinAlgError:
+        pass
+    d = float(np.abs(np.diag(H)).max())
+    shift = 1e-15 * d
+    for _ in range(12):
+        try:
+            return np.linalg.cholesky(H + shift * np.eye(H.shape[0])), shift
+        except np.linalg.LinAlgError:
+            shift *= 10.0
+    raise np.linalg.LinAlgError("H not positive definite even with a 1e-3 relative shift")
+
+
+def solve_ipm(p: NrmpProblem, max_iter: int = 60, tol: float = 1e-11, verbose: bool = False, info: dict | None = None):
+    """Returns S, U, D, iterations.  Termination: complementarity gap < tol and dual residual < 100*tol
+    *relative to the problem's gradient scale*; an iteration that stalls in rounding noise below the
+    acceptance level (gap < 1e-9, relative residual < 1e-8: still 4 orders below the 1e-4 parity budget)
+    returns its best iterate; anything else raises IpmFailure (callers fall back to HiGHS)."""
     m_ = assemble(p)
     P, c, Ab, bb, J, k, rho = m_["P"], m_["c"], m_["Ab"], m_["bb"], m_["J"], m_["k"], m_["rho"]
     n, nU, nD, s0, F, T, M = m_["n"], m_["nU"], m_["nD"], m_["s0"], m_["F"], m_["T"], m_["M"]
@@ -114,21 +140,38 @@ def solve_ipm(p: NrmpProblem, max_iter: int = 60, tol: float = 1e-11, verbose: b
     z_b, z_w, z_r = 1.0 / sb_, 1.0 / s_w, 1.0 / s_r
     m_tot = len(bb) + 2 * T * M
 
+    # gradient scale of the problem: the residual test is relative to it (an env whose cost gradient is
+    # O(1e3) cannot reach an absolute 1e-9 in float64 -- C4 env 934, iteration 5, was the counter-example)
+    scale = max(1.0, float(np.abs(c).max()), float(rho * np.abs(k).max()) if M > 0 and k.size else 0.0)
+    best = None  # (merit, x, it)
     it = 0
+    status = "max_iter"
     for it in range(max_iter):
         rd_x = P @ x + c + Ab.T @ z_b + J.T @ z_r
         rd_w = rho * w - z_w - z_r
         gap = (sb_ @ z_b + s_w @ z_w + s_r @ z_r) / max(m_tot, 1)
-        res = max(np.abs(rd_x).max(), np.abs(rd_w).max() if M > 0 else 0.0)
+        res = max(np.abs(rd_x).max(), np.abs(rd_w).max() if M > 0 else 0.0) / scale
         if verbose:
             print(it, gap, res)
+        if gap < 1e-9 and res < 1e-8:
+            merit = max(gap, res * 1e-1)
+            if best is None or merit < best[0]:
+                best = (merit, x.copy(), it)
+            elif it - best[2] >= 3:  # three iterations without progress below the acceptance level: rounding floor
+                status = "stalled"
+                break
         if gap < tol and res < tol * 100:
+            status = "converged"
             break
         W_b, W_w, W_r = z_b / sb_, z_w / s_w, z_r / s_r
         Hww = rho + W_w + W_r
         omega = W_r * (rho + W_w) / Hww
         H = P + Ab.T @ (W_b[:, None] * Ab) + J.T @ (omega[:, None] * J)
-        Lc = np.linalg.cholesky(H)
+        try:
+            Lc, _shift = _guarded_cholesky(H)
+        except np.linalg.LinAlgError:
+            status = "cholesky"
+            break
 
         def newton(rc_b, rc_w, rc_r):
             v_b, v_w, v_r = rc_b / sb_, rc_w / s_w, rc_r / s_r
@@ -169,6 +212,12 @@ def solve_ipm(p: NrmpProblem, max_iter: int = 60, tol: float = 1e-11, verbose: b
         sb_, s_w, s_r = sb_ + a * ds[0], s_w + a * ds[1], s_r + a * ds[2]
         z_b, z_w, z_r = z_b + a * dz[0], z_w + a * dz[1], z_r + a * dz[2]
 
+    if status != "converged":
+        if best is None:
+            raise IpmFailure(f"interior point method ended with status {status} at iteration {it} (gap {gap:.2e}, rel. residual {res:.2e})")
+        x = best[1]
+    if info is not None:
+        info.update(status=status, iterations=it, gap=float(gap), residual=float(res), scale=scale)
     U = x[:nU].reshape(T, 2).T.copy()
     S = np.zeros((3, T + 1))
     S[:, 0] = p.nom_s[:, 0]

@@ -35,6 +35,7 @@ class OraclePAN:
         self.iters_run = 0
         self.t_dune = 0.0
         self.t_nrmp = 0.0
+        self.fallbacks = 0
         self.trace = []
 
     def _solve(self, prob):
@@ -43,7 +44,15 @@ class OraclePAN:
             if not ok:
                 raise RuntimeError("HiGHS did not report optimal")
             return S, U, D
-        S, U, D, _ = oipm.solve_ipm(prob)
+        try:
+            S, U, D, _ = oipm.solve_ipm(prob)
+        except (oipm.IpmFailure, np.linalg.LinAlgError, ValueError):
+            # second solver of the same program (HiGHS active set on the lifted form); counted so that
+            # callers can report how often the oracle of record had to be replaced
+            self.fallbacks += 1
+            S, U, D, ok = onrmp.solve_highs(prob)
+            if not ok:
+                raise RuntimeError("neither the interior point method nor HiGHS solved this NRMP instance")
         return S, U, D
 
     def forward(self, nom_s, nom_u, ref_s, ref_us, obs_points=None, point_velocities=None, keep_trace=False):
