@@ -79,12 +79,33 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU path (the oracle port of the reference: oracle/pan.py) -- cpu_baseline and --impl reference
 # --------------------------------------------------------------------------------------------
-def host_cores() -> int:
-    """Cores this process may actually run on (cgroup / affinity aware), not the machine's total."""
+def cpu_quota_cores():
+    """CPU-time quota of this container in cores (cgroup v2 cpu.max / v1 cfs quota), or None when unlimited.
+    The round-2 GPU box showed 128 logical CPUs in its affinity mask but handed 128 busy workers only ~16 cores of
+    CPU time (wall-clock rate 95 env-steps/s, rate from the workers' own CPU time 760): the quota is what counts."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else float(q) / float(p)
+    except (OSError, ValueError):
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / p
+    except (OSError, ValueError):
+        return None
+
+
+def host_cores() -> int:
+    """Worker processes to start = cores this process can actually use: affinity mask, capped by the cgroup CPU quota."""
+    try:
+        n = max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    q = cpu_quota_cores()
+    if q is not None:
+        n = max(1, min(n, int(q + 0.5)))
+    return n
 
 
 def _cpu_worker(args):
@@ -166,7 +187,8 @@ def cpu_sample(cname: str, K: int, iter_threshold: float, rounds: int, envs_per_
                    failed_envs=sum(r["failed"] for r in runs), highs_fallback_solves=sum(r["fallbacks"] for r in runs),
                    rate_per_round=rates, spread=(max(rates) - min(rates)) / max(rates) if rates else None, wall_s=sum(walls),
                    dune_ms_per_env=mean("dune_ms_per_env"), nrmp_ms_per_env=mean("nrmp_ms_per_env"), pan_iterations_per_env=mean("iters_per_env"),
-                   env_steps_per_s_per_core=envs / sum(walls) / cores, rate_from_cpu_time=float(np.mean([r["rate_from_cpu_time"] for r in runs])))
+                   env_steps_per_s_per_core=envs / sum(walls) / cores, rate_from_cpu_time=float(np.mean([r["rate_from_cpu_time"] for r in runs])),
+                   effective_cores=float(np.mean([r['rate'] / max(r['rate_from_cpu_time'], 1e-9) for r in runs])) * cores, logical_cpus=os.cpu_count(), affinity_cpus=len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None, cgroup_quota_cores=cpu_quota_cores())
     return summary, runs
 
 
@@ -195,7 +217,8 @@ def run_reference(args):
                 cpu_baseline=dict(value=value, unit=UNIT, cores=summ["cores"], kind="port",
                                   sample=f"{summ['envs_per_round']} envs/step x {steps} steps of {args.workload} (8 envs per worker process, {summ['cores']} processes, warm-up = 1 env per worker); {CPU_WHAT}",
                                   **{k: summ[k] for k in ("failed_envs", "highs_fallback_solves", "rate_per_round", "spread", "dune_ms_per_env", "nrmp_ms_per_env",
-                                                           "pan_iterations_per_env", "env_steps_per_s_per_core", "rate_from_cpu_time")}),
+                                                           "pan_iterations_per_env", "env_steps_per_s_per_core", "rate_from_cpu_time", "logical_cpus", "affinity_cpus",
+                                                           "cgroup_quota_cores", "effective_cores")}),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 

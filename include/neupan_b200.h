@@ -40,7 +40,7 @@ enum {
   NB_STATUS_OK = 0,
   NB_STATUS_MAXITER = 1,     /* interior point method hit its iteration cap */
   NB_STATUS_NUMERIC = 2,     /* non-finite value / failed factorisation */
-  NB_STATUS_INFEASIBLE = 4   /* empty bounds (d_min > d_max, max_speed <= 0, max_acce <= 0) */
+  NB_STATUS_INFEASIBLE = 4   /* empty bounds (d_min > d_max, max_speed <= 0, max_acce <= 0); d_min == d_max is feasible: D is fixed */
 };
 
 typedef struct nb_pan nb_pan_t; /* opaque; owns weights, workspaces and the per-env state of
@@ -53,7 +53,7 @@ typedef struct {
   int32_t kinematics;     /* NB_KIN_*     robot.py:34,60                             */
   int32_t edge_dim;       /* E = rows of G (3..8)   dune.py:47                       */
   int32_t iter_num;       /* K            pan.py:48                                  */
-  int32_t nrmp_max_num;   /* M (0 => no_obs, pan.py:85)                              */
+  int32_t nrmp_max_num;   /* M (0 => no_obs, pan.py:85); receding <= 32, M <= 32 and receding * M <= 256 */
   int32_t max_envs;       /* capacity: largest B of any later call                   */
   int32_t max_points;     /* capacity: largest N of any later call (after decimation) */
   int32_t device;         /* CUDA device ordinal                                     */
@@ -116,14 +116,18 @@ int nb_pan_set_iteration(nb_pan_t* pan, int32_t iter_num, float iter_threshold);
  * 0 = all-FP32 FFMA kernel, kept as the in-tree numerical reference of the same contract (needs the edge count
  * compiled in).
  * NB_OPT_OVERLAP: 1..4 = number of environment sub-batches pipelined on internal streams so that the DUNE kernel
- * of one sub-batch shares the SMs with the NRMP kernel of another (results are identical; envs are independent). */
-enum { NB_OPT_DUNE_KERNEL = 1, NB_OPT_OVERLAP = 2 };
+ * of one sub-batch shares the SMs with the NRMP kernel of another (results are identical; envs are independent).
+ * NB_OPT_NRMP_WARM: 1 (default) = inside one nb_pan_forward the NRMP solve of PAN iteration k > 0 starts from the solution of
+ * iteration k-1 of the same environment (fewer interior point iterations, same optimum to the solver tolerance); 0 = every
+ * solve starts cold.  The first solve of every call is always cold, so results never depend on earlier calls. */
+enum { NB_OPT_DUNE_KERNEL = 1, NB_OPT_OVERLAP = 2, NB_OPT_NRMP_WARM = 3 };
 int nb_pan_set_option(nb_pan_t* pan, int32_t option, int32_t value);
 
 /* Forget PAN.current_nom_values (pan.py:100-105) of all environments.  (The reference's
  * neupan.reset() does NOT do this, neupan/neupan.py:288-294; exposed for tests and for
  * re-using a handle on a new batch.) */
-int nb_pan_reset_state(nb_pan_t* pan);
+int nb_pan_reset_state(nb_pan_t* pan);                      /* legacy default stream, returns after completion */
+int nb_pan_reset_state_async(nb_pan_t* pan, void* stream);   /* ordered with the forwards enqueued on `stream` */
 
 /* The sorted selections of the last executed iteration, what DUNE.forward returns restricted to
  * the first M columns (dune.py:100-104): mu (B,T+1,M,E) lam (B,T+1,M,2) points (B,T+1,M,2)
@@ -215,7 +219,8 @@ int nb_ipath_step(nb_ipath_t* ip, int32_t B, const double* states, const float* 
 
 /* neupan.reset (neupan/neupan.py:287-294): point_index = curve_index = 0, arrive_flag = False for every environment.
  * The path headings rewritten so far stay as they are (as in the reference). */
-int nb_ipath_reset(nb_ipath_t* ip);
+int nb_ipath_reset(nb_ipath_t* ip);                       /* legacy default stream, returns after completion */
+int nb_ipath_reset_async(nb_ipath_t* ip, void* stream);   /* ordered with the steps enqueued on `stream` */
 
 /* Persistent per-environment indices and a copy of the (mutated) path points; any pointer may be NULL.  DEVICE pointers
  * for the indices (B) int32, HOST pointer for points (P,4) float64 (synchronises `stream`). */

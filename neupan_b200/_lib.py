@@ -19,6 +19,7 @@ NB_OK, NB_ERR_INVALID, NB_ERR_CUDA, NB_ERR_CAPACITY, NB_ERR_NO_DEVICE = 0, -1, -
 STATUS_MAXITER, STATUS_NUMERIC, STATUS_INFEASIBLE = 1, 2, 4
 OPT_DUNE_KERNEL = 1
 OPT_OVERLAP = 2
+OPT_NRMP_WARM = 3
 
 
 class PanConfig(C.Structure):
@@ -64,6 +65,7 @@ SYMBOLS = {
     "nb_pan_set_iteration": (C.c_int, [C.c_void_p, C.c_int32, C.c_float]),
     "nb_pan_set_option": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "nb_pan_reset_state": (C.c_int, [C.c_void_p]),
+    "nb_pan_reset_state_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nb_pan_read_selection": (C.c_int, [C.c_void_p, C.c_int32] + [_FP] * 5 + [C.c_void_p]),
     "nb_pan_read_diagnostics": (C.c_int, [C.c_void_p, C.c_int32, _FP, C.c_void_p]),
     "nb_dune_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [_FP] * 5 + [C.c_void_p]),
@@ -74,6 +76,7 @@ SYMBOLS = {
     "nb_ipath_set_paths": (C.c_int, [C.c_void_p, C.c_int32, _FP, C.c_int64, _FP, C.c_int32, _FP, _FP]),
     "nb_ipath_step": (C.c_int, [C.c_void_p, C.c_int32, _FP, _FP, C.c_double, _FP, _FP, _FP, _FP, _FP, C.c_void_p]),
     "nb_ipath_reset": (C.c_int, [C.c_void_p]),
+    "nb_ipath_reset_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nb_ipath_read_state": (C.c_int, [C.c_void_p, C.c_int32, _FP, _FP, _FP, _FP, C.c_void_p]),
     "nb_launch_count": (C.c_int64, []),
     "nb_last_error": (C.c_char_p, []),

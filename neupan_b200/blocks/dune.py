@@ -42,12 +42,18 @@ class DUNE(torch.nn.Module):
             if train_kwargs and train_kwargs.get("direct_train", False):
                 return
             raise FileNotFoundError("DUNE checkpoint is required (pan.dune_checkpoint); training on demand is not part of the hot path")
-        if str(checkpoint).endswith(".npz"):
+        try:
             path = file_check(checkpoint)
+        except FileNotFoundError:
+            # dune.py:146-170: a named but missing checkpoint is not fatal when the caller asked to train directly
+            if train_kwargs and train_kwargs.get("direct_train", False):
+                print(f"checkpoint {checkpoint} not found; direct_train is set: weights stay at their initial values until train_dune()")
+                return
+            raise
+        if str(checkpoint).endswith(".npz"):
             z = np.load(path)
             sd = {k: torch.from_numpy(z[k]) for k in z.files if k.startswith("MLP.")}
         else:
-            path = file_check(checkpoint)
             sd = torch.load(path, map_location=torch.device("cpu"))
         self.abs_checkpoint_path = path
         self.model.load_state_dict(sd)
@@ -71,6 +77,7 @@ class DUNE(torch.nn.Module):
         self.train_model = DUNETrain(self.model, self.G, self.h, path)
         self.full_model_name = self.train_model.start(**train_kwargs)
         print("Complete Training. The model is saved in " + str(self.full_model_name))
+        self.weights_version = getattr(self, "weights_version", 0) + 1  # PAN re-packs the native weight image on the next forward
         return self.full_model_name
 
     @property

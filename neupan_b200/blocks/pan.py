@@ -64,6 +64,7 @@ class PAN(torch.nn.Module):
         self.device = torch.device("cuda", dev.index if dev.index is not None else 0)
         self._handle = None
         self.overlap = int(kwargs.get("overlap", 1))  # env sub-batches pipelined on internal streams (1 = off)
+        self.nrmp_warm = int(kwargs.get("nrmp_warm", 1))  # 1 = NRMP solves of PAN iterations k > 0 start from iteration k-1's solution
         self.dune_kernel = int(kwargs.get("dune_kernel", 2))  # 2 = tcgen05 DUNE kernel (default), 1 = mma.sync, 0 = all-FP32 FFMA
         self._cap = (max(1, int(kwargs.get("max_envs", 1))), max(1, int(kwargs.get("max_points", max(1, dune_max_num)))))
         self._sent = None  # (adjust version, iter_num, iter_threshold) last pushed to the handle
@@ -93,8 +94,16 @@ class PAN(torch.nn.Module):
     def _ensure_handle(self, B: int, N: int):
         lib = _lib.load()
         cap_b, cap_n = self._cap
+        wv = getattr(self.dune_layer, "weights_version", 0) if self.dune_layer is not None else 0
+        if self._handle is not None and wv != getattr(self, "_weights_version", 0):
+            self.close()  # DUNE.train_dune produced new weights: rebuild the native weight images
+        self._weights_version = wv
         if self._handle is not None and B <= cap_b and N <= cap_n:
             return lib
+        if self._handle is not None:
+            # the stop criterion's memory (PAN.current_nom_values, pan.py:100-105) lives in the native handle and is dropped here
+            print(f"neupan_b200.PAN: capacity grows to max_envs={max(cap_b, B)}, max_points={max(cap_n, N)}; the native handle is re-created "
+                  "and the stop-criterion state of all environments is reset (pass max_envs / max_points up front to avoid this)")
         self.close()
         cap_b, cap_n = max(cap_b, B), max(cap_n, N)
         cfg = self._config(cap_b, cap_n)
@@ -113,6 +122,7 @@ class PAN(torch.nn.Module):
         if not self.no_obs:
             _lib.check(lib.nb_pan_set_option(handle, _lib.OPT_DUNE_KERNEL, int(self.dune_kernel)))
         _lib.check(lib.nb_pan_set_option(handle, _lib.OPT_OVERLAP, int(self.overlap)))
+        _lib.check(lib.nb_pan_set_option(handle, _lib.OPT_NRMP_WARM, int(self.nrmp_warm)))
         self._sent = (self.nrmp_layer.version, int(self.iter_num), float(self.iter_threshold))
         return lib
 
@@ -141,7 +151,9 @@ class PAN(torch.nn.Module):
     def reset_state(self):
         """Forget the stop criterion's memory (PAN.current_nom_values, pan.py:100-105)."""
         if self._handle is not None:
-            _lib.check(_lib.load().nb_pan_reset_state(self._handle))
+            with torch.cuda.device(self.device):
+                stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+                _lib.check(_lib.load().nb_pan_reset_state_async(self._handle, stream))
 
     # ------------------------------------------------------------------ forward
     def forward(self, nom_s: torch.Tensor, nom_u: torch.Tensor, ref_s: torch.Tensor, ref_us: torch.Tensor,
@@ -161,9 +173,24 @@ class PAN(torch.nn.Module):
             obs_points = point_velocities = None
         elif obs_points.shape[-1] > self.dune_max_num:  # pan.py:171-174
             self.print_once(f"down sample the obs points from {obs_points.shape[-1]} to {self.dune_max_num}")
-            idx = torch.from_numpy(decimation_indices(obs_points.shape[-1], self.dune_max_num)).to(obs_points.device)
-            obs_points = obs_points.index_select(-1, idx)
-            point_velocities = None if point_velocities is None else point_velocities.index_select(-1, idx)
+            if num_points is None:
+                idx = torch.from_numpy(decimation_indices(obs_points.shape[-1], self.dune_max_num)).to(obs_points.device)
+                obs_points = obs_points.index_select(-1, idx)
+                point_velocities = None if point_velocities is None else point_velocities.index_select(-1, idx)
+            else:
+                # ragged batch: the reference decimates each environment's OWN n_b points (an unbatched call sees (2, n_b)),
+                # so the column pick is np.linspace(0, n_b-1, m).astype(int) per environment; envs with n_b <= m keep theirs
+                m = self.dune_max_num
+                nb = num_points.detach().to(device=obs_points.device, dtype=torch.int64).clamp(min=0, max=obs_points.shape[-1])
+                step = (nb - 1).to(torch.float64) / float(m - 1) if m > 1 else torch.zeros_like(nb, dtype=torch.float64)
+                idx = (torch.arange(m, device=obs_points.device, dtype=torch.float64)[None, :] * step[:, None]).to(torch.int64)  # numpy: arange * step, truncated
+                idx[:, -1] = nb - 1  # linspace pins its last sample to the stop value
+                keep = torch.arange(m, device=obs_points.device)[None, :].expand(B, m)
+                idx = torch.where((nb > m)[:, None], idx, keep).clamp_(min=0)
+                gidx = idx[:, None, :].expand(B, 2, m)
+                obs_points = obs_points.gather(-1, gidx)
+                point_velocities = None if point_velocities is None else point_velocities.gather(-1, gidx)
+                num_points = torch.minimum(nb, torch.full_like(nb, m)).to(torch.int32)
         N = obs_points.shape[-1] if use_points else 0
         lib = self._ensure_handle(B, N)
         self._push_settings(lib)

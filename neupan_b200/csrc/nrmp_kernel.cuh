@@ -7,13 +7,20 @@
 //                                                                              robot.py:73-236
 //   PAN.stop_criteria                                                          pan.py:215-243
 //
-// Method (derivation mirrored by the CPU checker oracle/ipm.py): the states are eliminated through
-// the linearised dynamics, s_{t+1} = s0_{t+1} + F_t u; the squared hinge of robot.py:183-198 is
-// lifted with slacks w_tm >= 0, w_tm >= D_t + fb_tm - fa_tm.s_{t+1,xy}; a Mehrotra
-// predictor-corrector primal-dual interior point method runs in FP64 from a strictly feasible
-// start.  Inside each Newton step the T*M hinge slacks and the T distances D_t are eliminated
-// analytically (both blocks are diagonal), so the only factorisation is a dense 2T x 2T Cholesky
-// in the warp's shared memory.
+// Method: the states are eliminated through the linearised dynamics, s_{t+1} = s0_{t+1} + F_t u.  The squared
+// hinge of robot.py:183-198,  (rho/2) max(0, r)^2 with r_tm = D_t + fb_tm - fa_tm.s_{t+1,xy},  is written as
+// min_w (rho/2) w^2 s.t. w >= r  -- ONE inequality per hinge (w >= 0 is redundant: for r <= 0 the unconstrained
+// minimiser w = 0 is feasible) -- and w is eliminated through its stationarity condition w = z/rho, z the row's
+// multiplier, so a hinge row carries only the pair (s, z) with  s = z/rho - r >= 0.  [The CPU checker oracle/ipm.py
+// keeps the textbook two-row lift (w >= 0, w >= r): every inactive hinge is then a degenerate pair (s_w, z_w -> 0
+// together like sqrt(mu)) and the interior point iteration converges linearly, ~16.5 iterations on C4; the one-row
+// form is non-degenerate, converges superlinearly at the end (~14 cold) and has half the hinge state.  The two
+// formulations are independent derivations of the same program -- their agreement is a parity check, not shared
+// algebra.]  A Mehrotra predictor-corrector primal-dual interior point method runs in FP64 from a strictly feasible
+// start: cold (u = 0, D mid-range) or WARM from the previous PAN iteration's solution of the same environment
+// (x pulled 5 % towards the centre, slacks recomputed from it, multipliers floored at mu0 / s): ~10 iterations.
+// Inside each Newton step the T*M hinge rows and the T distances D_t are eliminated analytically (both blocks are
+// diagonal), so the only factorisation is a dense 2T x 2T Cholesky in the warp's shared memory.
 //
 // Mapping: lanes own rows of the 2T x 2T system (triangular solves run in registers with
 // shuffles), lanes own HPL hinge rows each whose slack/multiplier state lives in registers, lanes
@@ -44,8 +51,12 @@ struct NrmpParams {
   int32_t* active;      // (B) or nullptr: envs with 0 are skipped; cleared when the stop test fires
   // PAN.current_nom_values (pan.py:100-105), per env; nullptr disables the stop criterion
   float* prev_s; float* prev_u; float* prev_mu; float* prev_lam; int32_t* prev_count; int32_t* prev_valid;
+  // warm start (NB_OPT_NRMP_WARM): per-env float record [x (2T) | D (T) | z of the box/rate/D rows (mb) | z of the hinge rows (T*M)]
+  // of the last converged solve; warm_valid[b] != 0 marks it usable.  nullptr = always cold.
+  float* warm; int32_t* warm_valid;
   int B, T, M, E, kin;
   int max_ipm_iter;
+  double gap_tol;  // mean complementarity at termination (1e-13: the one-row hinge form needs it for 1e-7 accuracy in u)
   float iter_threshold;
   double dt, L;
   float q[3], p_u, eta, d_max, d_min;
@@ -82,6 +93,11 @@ __host__ __device__ inline size_t nrmp_warp_doubles(int T, int M) {
 __host__ __device__ inline size_t nrmp_cta_extra_bytes(int T) {  // pair table (uint16) shared by the CTA's warps
   const int nU = 2 * T;
   return (((size_t)nU * (nU + 1) / 2) * 2 + 15) / 16 * 16;
+}
+
+__host__ __device__ inline size_t nrmp_warm_floats(int T, int M) {
+  const int nU = 2 * T, nR = nU - 2, TD = M > 0 ? T : 0;
+  return (size_t)nU + TD + (2 * nU + 2 * nR + 2 * TD) + (size_t)T * M;
 }
 
 #define NB_LL(i, n) _Pragma("unroll 1") for (int i = lane; i < (n); i += 32)
@@ -205,14 +221,17 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
   const int rows_s = omni ? 2 : 3;
   const bool en_speed[2] = {isfinite(prm.speed[0]), isfinite(prm.speed[1])};
   const bool en_acce[2] = {isfinite(prm.acce[0]), isfinite(prm.acce[1])};
+  const double rho = prm.ro, eta = (double)prm.eta;
+  const double dlo = fmax((double)prm.d_min, 0.0), dhi = (double)prm.d_max;
+  const bool dfix = TD > 0 && dhi == dlo;  // d_max == d_min: D is a constant, its bound rows and its Newton block drop out
   NB_LL(k, mb) {  // rows of the shared-memory constraint block that are switched on
-    bool on = true;
+    bool on = !dfix;  // D rows
     if (k < oRU) on = en_speed[(k % nU) & 1];
     else if (k < oDU) on = en_acce[((k - oRU) % nR) & 1];
     cen[k] = on ? 1 : 0;
   }
   auto enabled = [&](int k) -> bool { return cen[k] != 0; };
-  int m_active = 2 * TD + 2 * TM;
+  int m_active = (dfix ? 0 : 2 * TD) + TM;
   for (int c = 0; c < 2; ++c) m_active += (en_speed[c] ? 2 * T : 0) + (en_acce[c] ? 2 * (T - 1) : 0);
   const double inv_m = 1.0 / (double)(m_active > 0 ? m_active : 1);
 
@@ -301,19 +320,16 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
   __syncwarp();  // the linearisation data in `scratch` is dead from here on
 
   // ---- 4. obstacle coefficients (nrmp.py:220-261), hinge rows owned by lanes -----------------------
-  const double rho = prm.ro, eta = (double)prm.eta;
-  const double dlo = fmax((double)prm.d_min, 0.0), dhi = (double)prm.d_max;
   const int cnt = (prm.fa || M == 0) ? M : (prm.sel_count ? prm.sel_count[b] : 0);
-  float hfx[HPL], hfy[HPL];
-  double hsw[HPL], hsr[HPL], hzw[HPL], hzr[HPL], hdsw[HPL], hdsr[HPL], hdzw[HPL], hdzr[HPL];
-  float hisw[HPL], hisr[HPL];
-  int hts[HPL];  // horizon step of each owned hinge row
-  double hih[HPL];  // 1/H_ww must be FP64: the slack elimination has to be exact for the Newton system to stay consistent
+  float hfx[HPL], hfy[HPL], his[HPL];
+  double hs[HPL], hz[HPL], hds[HPL], hdz[HPL], hkk[HPL];
+  int hts[HPL];     // horizon step of each owned hinge row
+  double hih[HPL];  // 1/(rho + W) in FP64: the hinge elimination has to be exact for the Newton system to stay consistent
 #pragma unroll
   for (int q_ = 0; q_ < HPL; ++q_) {
     const int k = lane + 32 * q_;
-    hts[q_] = 0; hfx[q_] = 0.f; hfy[q_] = 0.f; hsw[q_] = 1.0; hsr[q_] = 1.0; hzw[q_] = 0.0; hzr[q_] = 0.0;
-    hdsw[q_] = hdsr[q_] = hdzw[q_] = hdzr[q_] = 0.0; hisw[q_] = hisr[q_] = 0.f; hih[q_] = 0.0;
+    hts[q_] = 0; hfx[q_] = 0.f; hfy[q_] = 0.f; hs[q_] = 1.0; hz[q_] = 0.0; hkk[q_] = 0.0;
+    hds[q_] = hdz[q_] = 0.0; his[q_] = 0.f; hih[q_] = 0.0;
     if (k < TM) {
       const int t = k / M, mm = k - t * M;
       hts[q_] = t;
@@ -331,34 +347,74 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
       }
       hfx[q_] = fx; hfy[q_] = fy;
       fax_s[k] = fx; fay_s[k] = fy;
-      const double kk = (double)fbv - ((double)fx * s0[t] + (double)fy * s0[T + t]);
-      const double r = 0.5 * (dlo + dhi) + kk;  // hinge argument at the start (u = 0, D mid-range)
-      const double w = fmax(r, 0.0) + 1.0;
-      hsw[q_] = w; hsr[q_] = w - r; hzw[q_] = 1.0 / w; hzr[q_] = 1.0 / (w - r);
+      hkk[q_] = (double)fbv - ((double)fx * s0[t] + (double)fy * s0[T + t]);  // hinge argument at u = 0, without D_t
     }
   }
 
-  // ---- 5. strictly feasible start of the remaining rows --------------------------------------------
+  // ---- 5. strictly feasible start: cold (u = 0, D mid-range) or warm (previous solve of this environment) ------
   int stat = 0;
-  if (TD > 0 && !(dhi > dlo)) stat |= 4;
+  if (TD > 0 && dhi < dlo) stat |= 4;
   for (int c = 0; c < 2; ++c) {
     if (en_speed[c] && !(prm.speed[c] > 0)) stat |= 4;
     if (en_acce[c] && !(prm.acce[c] > 0)) stat |= 4;
   }
+  const size_t warm_floats = nrmp_warm_floats(T, M);
+  float* wrec = prm.warm ? prm.warm + (size_t)b * warm_floats : nullptr;
+  const bool warm = wrec != nullptr && prm.warm_valid[b] != 0 && stat == 0;
+  const double dmid = 0.5 * (dlo + dhi);
+  constexpr double kTheta = 0.05, kMu0 = 1e-2, kDw = 0.03;  // measured on C4 / C2 problem sequences: DESIGN.md 3.2
+  NB_LL(i, nU) x[i] = warm ? (1.0 - kTheta) * (double)wrec[i] : 0.0;
+  NB_LL(t, TD) Dv[t] = dfix ? dlo : (warm ? (1.0 - kTheta) * (double)wrec[nU + t] + kTheta * dmid : dmid);
+  __syncwarp();
   NB_LL(i, nU) {
-    x[i] = 0.0;
     const int c = i & 1;
-    cs[oBU + i] = en_speed[c] ? prm.speed[c] : 1.0; cs[oBL + i] = cs[oBU + i];
-    cz[oBU + i] = en_speed[c] ? 1.0 / cs[oBU + i] : 0.0; cz[oBL + i] = cz[oBU + i];
+    const double xi = x[i];
+    const double su = en_speed[c] ? prm.speed[c] - xi : 1.0, sl = en_speed[c] ? prm.speed[c] + xi : 1.0;
+    cs[oBU + i] = su; cs[oBL + i] = sl;
+    double zu = en_speed[c] ? (warm ? kMu0 : 1.0) / su : 0.0, zl = en_speed[c] ? (warm ? kMu0 : 1.0) / sl : 0.0;
+    if (warm && en_speed[c]) { zu = fmax(zu, (double)wrec[nU + TD + oBU + i]); zl = fmax(zl, (double)wrec[nU + TD + oBL + i]); }
+    cz[oBU + i] = zu; cz[oBL + i] = zl;
     if (i < nR) {
-      cs[oRU + i] = en_acce[c] ? prm.acce[c] : 1.0; cs[oRL + i] = cs[oRU + i];
-      cz[oRU + i] = en_acce[c] ? 1.0 / cs[oRU + i] : 0.0; cz[oRL + i] = cz[oRU + i];
+      const double dd = x[i + 2] - xi;
+      const double ru = en_acce[c] ? prm.acce[c] - dd : 1.0, rl = en_acce[c] ? prm.acce[c] + dd : 1.0;
+      cs[oRU + i] = ru; cs[oRL + i] = rl;
+      double yu = en_acce[c] ? (warm ? kMu0 : 1.0) / ru : 0.0, yl = en_acce[c] ? (warm ? kMu0 : 1.0) / rl : 0.0;
+      if (warm && en_acce[c]) { yu = fmax(yu, (double)wrec[nU + TD + oRU + i]); yl = fmax(yl, (double)wrec[nU + TD + oRL + i]); }
+      cz[oRU + i] = yu; cz[oRL + i] = yl;
     }
   }
   NB_LL(t, TD) {
-    Dv[t] = 0.5 * (dlo + dhi);
-    cs[oDU + t] = dhi - Dv[t]; cs[oDL + t] = Dv[t] - dlo;
-    cz[oDU + t] = 1.0 / cs[oDU + t]; cz[oDL + t] = 1.0 / cs[oDL + t];
+    if (dfix) {
+      cs[oDU + t] = cs[oDL + t] = 1.0; cz[oDU + t] = cz[oDL + t] = 0.0;
+    } else {
+      const double su = dhi - Dv[t], sl = Dv[t] - dlo;
+      cs[oDU + t] = su; cs[oDL + t] = sl;
+      double zu = (warm ? kMu0 : 1.0) / su, zl = (warm ? kMu0 : 1.0) / sl;
+      if (warm) { zu = fmax(zu, (double)wrec[nU + TD + oDU + t]); zl = fmax(zl, (double)wrec[nU + TD + oDL + t]); }
+      cz[oDU + t] = zu; cz[oDL + t] = zl;
+    }
+    // position offset F x of the start (zero when cold): qx / qy are free until the first Newton solve
+    double ax = 0, ay = 0;
+    if (warm) {
+      const double* fxp = F + t * (t + 1);
+      const double* fyp = fxp + FT;
+      for (int i = 0; i < 2 * (t + 1); ++i) { ax += fxp[i] * x[i]; ay += fyp[i] * x[i]; }
+    }
+    qx[t] = ax; qy[t] = ay;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q_ = 0; q_ < HPL; ++q_) {
+    const int k = lane + 32 * q_;
+    if (k < TM) {
+      const int t = hts[q_];
+      const double r = Dv[t] + hkk[q_] - ((double)hfx[q_] * qx[t] + (double)hfy[q_] * qy[t]);
+      // s = z/rho - r > 0 needs z > rho r; rows far on the inactive side may start with a small multiplier
+      double z;
+      if (warm) z = fmax(fmax((double)wrec[nU + TD + mb + k], rho * fmax(r + kDw, 0.0)), kMu0 / fmax(-r, kDw));
+      else z = fmax(rho * fmax(r + 0.1, 0.0), 1.0 / fmax(-r, 0.1));
+      hz[q_] = z; hs[q_] = z / rho - r;
+    }
   }
   __syncwarp();
 
@@ -372,7 +428,7 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
 #pragma unroll
       for (int q_ = 0; q_ < HPL; ++q_) {
         const int k = lane + 32 * q_;
-        if (k < TM) tmpk[k] = hzr[q_];
+        if (k < TM) tmpk[k] = hz[q_];
       }
       __syncwarp();
       NB_LL(t, TD) {
@@ -413,19 +469,15 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
         rdU[i] = acc;
         res = fmax(res, fabs(acc));
       }
-      NB_LL(t, TD) res = fmax(res, fabs(rdD[t]));
+      if (!dfix) NB_LL(t, TD) res = fmax(res, fabs(rdD[t]));
       NB_LL(k, mb) if (enabled(k)) gsum += cs[k] * cz[k];
 #pragma unroll
-      for (int q_ = 0; q_ < HPL; ++q_) {
-        if (lane + 32 * q_ < TM) {
-          gsum += hsw[q_] * hzw[q_] + hsr[q_] * hzr[q_];
-          res = fmax(res, fabs(rho * hsw[q_] - hzw[q_] - hzr[q_]));
-        }
-      }
+      for (int q_ = 0; q_ < HPL; ++q_)
+        if (lane + 32 * q_ < TM) gsum += hs[q_] * hz[q_];
       res = warp_max(res);
       const double gap = warp_sum(gsum) * inv_m;
       if (!(gap == gap) || !(res == res)) { stat |= 2; break; }
-      if (gap < 1e-10 && res < 1e-8) { converged = true; break; }
+      if (gap < prm.gap_tol && res < 1e-8) { converged = true; break; }
 
       // (b) barrier weights; hinge rows publish omega for the per-step reductions
       __syncwarp();
@@ -434,10 +486,10 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
       for (int q_ = 0; q_ < HPL; ++q_) {
         const int k = lane + 32 * q_;
         if (k < TM) {
-          hisw[q_] = rcpf(hsw[q_]); hisr[q_] = rcpf(hsr[q_]);
-          const double Ww = hzw[q_] * (double)hisw[q_], Wr = hzr[q_] * (double)hisr[q_];
-          hih[q_] = rcp64(rho + Ww + Wr);
-          tmpk[k] = Wr * (rho + Ww) * hih[q_];
+          his[q_] = rcpf(hs[q_]);
+          const double Wr = hz[q_] * (double)his[q_];
+          hih[q_] = rcp64(rho + Wr);
+          tmpk[k] = Wr * rho * hih[q_];  // omega: the row's weight in the reduced Hessian (bounded by rho)
         }
       }
       __syncwarp();
@@ -450,7 +502,7 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
           a00 += ofx * fx; a01 += ofx * fy; a11 += ofy * fy; b0 += ofx; b1 += ofy; nn += om;
         }
         const double hdd = nn + cz[oDU + t] * (double)cis[oDU + t] + cz[oDL + t] * (double)cis[oDL + t];
-        const double ih = rcp64(hdd);
+        const double ih = dfix ? 0.0 : rcp64(hdd);  // fixed D: no D block, dD = 0
         iHDD[t] = ih; n0[t] = b0; n1[t] = b1;
         N00[t] = a00 - b0 * b0 * ih; N01[t] = a01 - b0 * b1 * ih; N11[t] = a11 - b1 * b1 * ih;
       }
@@ -564,23 +616,20 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
       // (e) predictor (pass 0) and corrector (pass 1) share one Newton body
       NB_LL(k, mb) cdz[k] = enabled(k) ? -cs[k] * cz[k] : 0.0;
 #pragma unroll
-      for (int q_ = 0; q_ < HPL; ++q_) { hdzw[q_] = -hsw[q_] * hzw[q_]; hdzr[q_] = -hsr[q_] * hzr[q_]; }
+      for (int q_ = 0; q_ < HPL; ++q_) hdz[q_] = -hs[q_] * hz[q_];
       double alpha = 1.0;
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
         __syncwarp();
-        // hinge rows: b_w and y = (W_r/H_ww) b_w - v_r
-        double hbw[HPL];
+        // hinge rows: v = rc / s and their right-hand-side contribution y = -(rho / (rho + W)) v
+        double hv[HPL];
 #pragma unroll
         for (int q_ = 0; q_ < HPL; ++q_) {
           const int k = lane + 32 * q_;
-          hbw[q_] = 0.0;
+          hv[q_] = 0.0;
           if (k < TM) {
-            const double vw = hdzw[q_] * (double)hisw[q_], vr = hdzr[q_] * (double)hisr[q_];
-            const double rdw = rho * hsw[q_] - hzw[q_] - hzr[q_];
-            hbw[q_] = -rdw + vw + vr;
-            const double wrh = hzr[q_] * (double)hisr[q_] * hih[q_];
-            tmpk[k] = wrh * hbw[q_] - vr;
+            hv[q_] = hdz[q_] * (double)his[q_];
+            tmpk[k] = -rho * hih[q_] * hv[q_];
           }
         }
         __syncwarp();
@@ -675,13 +724,11 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
           if (k < TM) {
             const int t = hts[q_];
             const double Jdx = dD[t] - ((double)hfx[q_] * qx[t] + (double)hfy[q_] * qy[t]);
-            const double wrh = hzr[q_] * (double)hisr[q_] * hih[q_];
-            const double dw = hbw[q_] * hih[q_] + wrh * Jdx;
-            hdsw[q_] = dw; hdsr[q_] = dw - Jdx;
-            hdzw[q_] = (hdzw[q_] - hzw[q_] * hdsw[q_]) * (double)hisw[q_];
-            hdzr[q_] = (hdzr[q_] - hzr[q_] * hdsr[q_]) * (double)hisr[q_];
-            ratio = fmaxf(ratio, fmaxf(-(float)hdsw[q_] * hisw[q_], -(float)hdsr[q_] * hisr[q_]));
-            ratio = fmaxf(ratio, fmaxf(-(float)hdzw[q_] * rcpf(hzw[q_]), -(float)hdzr[q_] * rcpf(hzr[q_])));
+            const double Wr = hz[q_] * (double)his[q_];
+            const double dw = hih[q_] * (hv[q_] + Wr * Jdx);  // step of the eliminated w = z / rho
+            hds[q_] = dw - Jdx;   // s = z/rho - r stays exact: ds = dz/rho - J dx
+            hdz[q_] = rho * dw;
+            ratio = fmaxf(ratio, fmaxf(-(float)hds[q_] * his[q_], -(float)hdz[q_] * rcpf(hz[q_])));
           }
         }
         NB_LL(i, nU) {
@@ -711,16 +758,12 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
           NB_LL(k, mb) if (enabled(k)) ga += (cs[k] + amax * cds[k]) * (cz[k] + amax * cdz[k]);
 #pragma unroll
           for (int q_ = 0; q_ < HPL; ++q_)
-            if (lane + 32 * q_ < TM)
-              ga += (hsw[q_] + amax * hdsw[q_]) * (hzw[q_] + amax * hdzw[q_]) + (hsr[q_] + amax * hdsr[q_]) * (hzr[q_] + amax * hdzr[q_]);
+            if (lane + 32 * q_ < TM) ga += (hs[q_] + amax * hds[q_]) * (hz[q_] + amax * hdz[q_]);
           const double sr = fmax(warp_sum(ga) * inv_m, 0.0) / gap;
           const double smu = sr * sr * sr * gap;  // sigma * mu
           NB_LL(k, mb) cdz[k] = enabled(k) ? (-cs[k] * cz[k] + smu - cds[k] * cdz[k]) : 0.0;
 #pragma unroll
-          for (int q_ = 0; q_ < HPL; ++q_) {
-            hdzw[q_] = -hsw[q_] * hzw[q_] + smu - hdsw[q_] * hdzw[q_];
-            hdzr[q_] = -hsr[q_] * hzr[q_] + smu - hdsr[q_] * hdzr[q_];
-          }
+          for (int q_ = 0; q_ < HPL; ++q_) hdz[q_] = -hs[q_] * hz[q_] + smu - hds[q_] * hdz[q_];
         } else {
           alpha = ratio > 0.995f ? 0.995 / (double)ratio : 1.0;
         }
@@ -730,14 +773,23 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
       NB_LL(k, mb) if (enabled(k)) { cs[k] += alpha * cds[k]; cz[k] += alpha * cdz[k]; }
 #pragma unroll
       for (int q_ = 0; q_ < HPL; ++q_) {
-        if (lane + 32 * q_ < TM) {
-          hsw[q_] += alpha * hdsw[q_]; hsr[q_] += alpha * hdsr[q_];
-          hzw[q_] += alpha * hdzw[q_]; hzr[q_] += alpha * hdzr[q_];
-        }
+        if (lane + 32 * q_ < TM) { hs[q_] += alpha * hds[q_]; hz[q_] += alpha * hdz[q_]; }
       }
       __syncwarp();
     }
     if (!converged && !(stat & 2)) stat |= 1;
+  }
+  if (wrec) {  // the next PAN iteration of this environment starts from here (only from a converged solve)
+    __syncwarp();
+    if (stat == 0) {
+      NB_LL(i, nU) wrec[i] = (float)x[i];
+      NB_LL(t, TD) wrec[nU + t] = (float)Dv[t];
+      NB_LL(k, mb) wrec[nU + TD + k] = (float)cz[k];
+#pragma unroll
+      for (int q_ = 0; q_ < HPL; ++q_)
+        if (lane + 32 * q_ < TM) wrec[nU + TD + mb + lane + 32 * q_] = (float)hz[q_];
+    }
+    if (lane == 0) prm.warm_valid[b] = stat == 0 ? 1 : 0;
   }
 
   // ---- 7. outputs: S = s0 + F u, U, D cast to float32 (nrmp.py:145-148) --------------------------

@@ -85,6 +85,10 @@ struct nb_pan {
   float *prev_s = nullptr, *prev_u = nullptr, *prev_mu = nullptr, *prev_lam = nullptr;
   int32_t *prev_count = nullptr, *prev_valid = nullptr, *active = nullptr, *iters = nullptr, *status = nullptr, *ipm_it = nullptr;
   float* min_dist = nullptr;
+  float* warm = nullptr;            // NRMP warm-start records, nrmp_warm_floats(T, M) per environment
+  int32_t* warm_valid = nullptr;
+  int nrmp_warm = 1;                // NB_OPT_NRMP_WARM
+  double nrmp_gap_tol = 1e-13;      // NB_NRMP_GAP_TOL (developer switch, read once at create)
   // staging for the host-pointer entry point
   float *h_in = nullptr, *h_out = nullptr;  // device staging
   size_t h_in_floats = 0, h_out_floats = 0;
@@ -160,6 +164,7 @@ int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st) {
   const nb_pan_config& c = p->cfg;
   prm.T = c.receding; prm.M = c.nrmp_max_num; prm.E = c.edge_dim; prm.kin = c.kinematics;
   prm.max_ipm_iter = 60;
+  prm.gap_tol = p->nrmp_gap_tol;
   prm.iter_threshold = c.iter_threshold;
   prm.dt = c.step_time; prm.L = c.wheelbase;
   for (int i = 0; i < 3; ++i) prm.q[i] = c.q_s[i];
@@ -202,10 +207,11 @@ int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st) {
   return go(nb::nrmp_kernel<8, false, 0, 0>);
 }
 
-__global__ void init_run_kernel(int B, int32_t* active, int32_t* iters, int32_t* status, float* min_dist, int32_t* sel_count) {
+__global__ void init_run_kernel(int B, int32_t* active, int32_t* iters, int32_t* status, float* min_dist, int32_t* sel_count, int32_t* warm_valid) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
     active[i] = 1; iters[i] = 0; status[i] = 0;
+    warm_valid[i] = 0;  // the first NRMP solve of a forward() is cold: results do not depend on earlier calls
     min_dist[i] = __int_as_float(0x7f800000);
     sel_count[i] = 0;
   }
@@ -240,6 +246,8 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
   if (cfg->max_envs < 1 || cfg->max_points < 0) return fail(NB_ERR_INVALID, "max_envs >= 1 and max_points >= 0 required");
   if (!(cfg->step_time > 0)) return fail(NB_ERR_INVALID, "step_time must be positive");
   if (cfg->kinematics == NB_KIN_ACKER && !(cfg->wheelbase > 0)) return fail(NB_ERR_INVALID, "acker needs a positive wheelbase");
+  if (cfg->receding * cfg->nrmp_max_num > 256)
+    return fail(NB_ERR_CAPACITY, "receding * nrmp_max_num = %d exceeds 256 (the NRMP kernel keeps at most 8 hinge rows per lane)", cfg->receding * cfg->nrmp_max_num);
   const bool with_dune = cfg->nrmp_max_num > 0;
   if (with_dune) {
     if (cfg->edge_dim < 3 || cfg->edge_dim > nb::kMaxEdges) return fail(NB_ERR_INVALID, "edge_dim must be in 3..%d", nb::kMaxEdges);
@@ -291,6 +299,10 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
   NB_CUDA(dalloc(&p->ipm_it, B));
   NB_CUDA(cudaMemset(p->ipm_it, 0, B * sizeof(int32_t)));
   NB_CUDA(dalloc(&p->min_dist, B));
+  NB_CUDA(dalloc(&p->warm, B * nb::nrmp_warm_floats(cfg->receding, cfg->nrmp_max_num)));
+  NB_CUDA(dalloc(&p->warm_valid, B));
+  NB_CUDA(cudaMemset(p->warm_valid, 0, B * sizeof(int32_t)));
+  if (const char* e = getenv("NB_NRMP_GAP_TOL")) p->nrmp_gap_tol = atof(e);
   NB_CUDA(cudaMemset(p->prev_valid, 0, B * sizeof(int32_t)));
   NB_CUDA(cudaMemset(p->prev_count, 0, B * sizeof(int32_t)));
   NB_CUDA(cudaMemset(p->sel_count, 0, B * sizeof(int32_t)));
@@ -307,7 +319,8 @@ int nb_pan_destroy(nb_pan_t* p) {
   }
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   void* bufs[] = {p->d_tc_image, p->d_image, p->d_weights, p->sel_mu, p->sel_lam, p->sel_pts, p->sel_dist, p->sel_count, p->prev_s, p->prev_u, p->prev_mu,
-                  p->prev_lam, p->prev_count, p->prev_valid, p->active, p->iters, p->status, p->ipm_it, p->min_dist, p->h_in, p->h_out, p->h_np, p->h_io};
+                  p->prev_lam, p->prev_count, p->prev_valid, p->active, p->iters, p->status, p->ipm_it, p->min_dist, p->h_in, p->h_out, p->h_np, p->h_io,
+                  p->warm, p->warm_valid};
   for (void* b : bufs)
     if (b) cudaFree(b);
   delete p;
@@ -345,14 +358,25 @@ int nb_pan_set_option(nb_pan_t* p, int32_t option, int32_t value) {
     p->overlap = value;
     return NB_OK;
   }
+  if (option == NB_OPT_NRMP_WARM) {
+    if (value < 0 || value > 1) return fail(NB_ERR_INVALID, "NB_OPT_NRMP_WARM takes 0 or 1");
+    p->nrmp_warm = value;
+    return NB_OK;
+  }
   return fail(NB_ERR_INVALID, "unknown option %d", option);
 }
 
-int nb_pan_reset_state(nb_pan_t* p) {
+int nb_pan_reset_state_async(nb_pan_t* p, void* stream) {
   if (!p) return fail(NB_ERR_INVALID, "null handle");
   NB_CUDA(cudaSetDevice(p->cfg.device));
-  NB_CUDA(cudaMemset(p->prev_valid, 0, (size_t)p->cfg.max_envs * sizeof(int32_t)));
-  NB_CUDA(cudaMemset(p->prev_count, 0, (size_t)p->cfg.max_envs * sizeof(int32_t)));
+  NB_CUDA(cudaMemsetAsync(p->prev_valid, 0, (size_t)p->cfg.max_envs * sizeof(int32_t), (cudaStream_t)stream));
+  NB_CUDA(cudaMemsetAsync(p->prev_count, 0, (size_t)p->cfg.max_envs * sizeof(int32_t), (cudaStream_t)stream));
+  return NB_OK;
+}
+
+int nb_pan_reset_state(nb_pan_t* p) {
+  if (int rc = nb_pan_reset_state_async(p, nullptr)) return rc;
+  NB_CUDA(cudaStreamSynchronize(nullptr));
   return NB_OK;
 }
 
@@ -397,7 +421,7 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
   const int T = c.receding, T1 = T + 1;
   const bool with_dune = c.nrmp_max_num > 0 && points != nullptr && N > 0;  // pan.py:130
   const int tb = 128, gb = (B + tb - 1) / tb;
-  init_run_kernel<<<gb, tb, 0, st>>>(B, p->active, p->iters, p->status, p->min_dist, p->sel_count);
+  init_run_kernel<<<gb, tb, 0, st>>>(B, p->active, p->iters, p->status, p->min_dist, p->sel_count, p->warm_valid);
   ++g_launches;
   // the nominal trajectory lives in the output buffers and is updated in place every iteration
   NB_CUDA(cudaMemcpyAsync(out_s, nom_s, (size_t)B * 3 * T1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -431,6 +455,10 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
       n.prev_s = p->prev_s + (size_t)lo * 3 * T1s; n.prev_u = p->prev_u + (size_t)lo * 2 * T;
       n.prev_mu = p->prev_mu + (size_t)lo * T1s * Ms * Es; n.prev_lam = p->prev_lam + (size_t)lo * T1s * Ms * 2;
       n.prev_count = p->prev_count + lo; n.prev_valid = p->prev_valid + lo;
+      if (p->nrmp_warm) {
+        n.warm = p->warm + (size_t)lo * nb::nrmp_warm_floats(T, c.nrmp_max_num);
+        n.warm_valid = p->warm_valid + lo;
+      }
       n.B = nb_;
       if (int rc = launch_nrmp(p, n, s)) return rc;
     }
@@ -606,12 +634,19 @@ int nb_ipath_destroy(nb_ipath_t* p) {
   return NB_OK;
 }
 
-int nb_ipath_reset(nb_ipath_t* p) {
+int nb_ipath_reset_async(nb_ipath_t* p, void* stream) {
   if (!p) return fail(NB_ERR_INVALID, "nb_ipath_reset: null handle");
   NB_CUDA(cudaSetDevice(p->cfg.device));
-  NB_CUDA(cudaMemset(p->d_curve_index, 0, sizeof(int32_t) * p->cfg.max_envs));
-  NB_CUDA(cudaMemset(p->d_point_index, 0, sizeof(int32_t) * p->cfg.max_envs));
-  NB_CUDA(cudaMemset(p->d_arrive_flag, 0, sizeof(int32_t) * p->cfg.max_envs));
+  cudaStream_t st = (cudaStream_t)stream;
+  NB_CUDA(cudaMemsetAsync(p->d_curve_index, 0, sizeof(int32_t) * p->cfg.max_envs, st));
+  NB_CUDA(cudaMemsetAsync(p->d_point_index, 0, sizeof(int32_t) * p->cfg.max_envs, st));
+  NB_CUDA(cudaMemsetAsync(p->d_arrive_flag, 0, sizeof(int32_t) * p->cfg.max_envs, st));
+  return NB_OK;
+}
+
+int nb_ipath_reset(nb_ipath_t* p) {
+  if (int rc = nb_ipath_reset_async(p, nullptr)) return rc;
+  NB_CUDA(cudaStreamSynchronize(nullptr));
   return NB_OK;
 }
 

@@ -92,7 +92,9 @@ class InitialPathBatch:
 
     def reset(self):
         """neupan.reset (neupan.py:287-294)."""
-        _lib.check(_lib.load().nb_ipath_reset(self._handle))
+        with torch.cuda.device(self.device):
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(_lib.load().nb_ipath_reset_async(self._handle, stream))
 
     def read_state(self):
         dev, B = self.device, self.B
