@@ -117,9 +117,9 @@ int nb_pan_set_iteration(nb_pan_t* pan, int32_t iter_num, float iter_threshold);
  * compiled in).
  * NB_OPT_OVERLAP: 1..4 = number of environment sub-batches pipelined on internal streams so that the DUNE kernel
  * of one sub-batch shares the SMs with the NRMP kernel of another (results are identical; envs are independent).
- * NB_OPT_NRMP_WARM: 1 (default) = inside one nb_pan_forward the NRMP solve of PAN iteration k > 0 starts from the solution of
- * iteration k-1 of the same environment (fewer interior point iterations, same optimum to the solver tolerance); 0 = every
- * solve starts cold.  The first solve of every call is always cold, so results never depend on earlier calls. */
+ * NB_OPT_NRMP_WARM: 1 = inside one nb_pan_forward the NRMP solve of PAN iteration k > 0 starts from the solution of
+ * iteration k-1 of the same environment (fewer interior point iterations on average, same optimum to the solver tolerance;
+ * a warm start that is not converging by its 12th iteration is abandoned for a cold one); 0 (default) = every solve starts cold.  The first solve of every call is always cold, so results never depend on earlier calls. */
 enum { NB_OPT_DUNE_KERNEL = 1, NB_OPT_OVERLAP = 2, NB_OPT_NRMP_WARM = 3 };
 int nb_pan_set_option(nb_pan_t* pan, int32_t option, int32_t value);
 

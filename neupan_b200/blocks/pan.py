@@ -64,7 +64,7 @@ class PAN(torch.nn.Module):
         self.device = torch.device("cuda", dev.index if dev.index is not None else 0)
         self._handle = None
         self.overlap = int(kwargs.get("overlap", 1))  # env sub-batches pipelined on internal streams (1 = off)
-        self.nrmp_warm = int(kwargs.get("nrmp_warm", 1))  # 1 = NRMP solves of PAN iterations k > 0 start from iteration k-1's solution
+        self.nrmp_warm = int(kwargs.get("nrmp_warm", 0))  # 1 = NRMP solves of PAN iterations k > 0 start from iteration k-1's solution (fewer IPM iterations on average, but stragglers: DESIGN.md 3.2)
         self.dune_kernel = int(kwargs.get("dune_kernel", 2))  # 2 = tcgen05 DUNE kernel (default), 1 = mma.sync, 0 = all-FP32 FFMA
         self._cap = (max(1, int(kwargs.get("max_envs", 1))), max(1, int(kwargs.get("max_points", max(1, dune_max_num)))))
         self._sent = None  # (adjust version, iter_num, iter_threshold) last pushed to the handle

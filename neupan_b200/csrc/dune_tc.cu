@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "dune_tc_kernel.cuh"
+#include "dune_tc8_kernel.cuh"
 
 namespace nb {
 
@@ -108,8 +109,9 @@ int build_tc_image(const float* w, int E, std::vector<unsigned char>& out) {
   return amax <= 30.0 ? 1 : 0;
 }
 
-int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int image_flags, int sm_count, int max_smem_optin, cudaStream_t st, char* err, size_t errlen) {
-  size_t smem = dune_tc_smem_bytes(prm.N, prm.geo.E, prm.M);
+int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int image_flags, int variant, int sm_count, int max_smem_optin, cudaStream_t st, char* err,
+                   size_t errlen) {
+  size_t smem = variant == 3 ? dune_tc8_smem_bytes(prm.N, prm.geo.E, prm.M) : dune_tc_smem_bytes(prm.N, prm.geo.E, prm.M);
   if ((long long)smem > max_smem_optin) {
     snprintf(err, errlen, "N=%d needs %zu B of shared memory (limit %d)", prm.N, smem, max_smem_optin);
     return -3;
@@ -120,13 +122,19 @@ int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int imag
     const char* v = getenv("NB_DUNE_TC");
     force = v ? atoi(v) : 0;
   }
-  const bool single = force == 1;
+  static int blocks8 = -1;  // NB_DUNE_TC8_BLOCKS: CTAs per SM of the 8-warp kernel (3: <= 85 registers, 4: <= 64 registers)
+  if (blocks8 < 0) {
+    const char* v = getenv("NB_DUNE_TC8_BLOCKS");
+    blocks8 = v ? atoi(v) : 3;
+    if (blocks8 != 4) blocks8 = 3;
+  }
+  const bool single = force == 1 && variant != 3;
   const bool barrier_sync = force != 2;  // default: block barrier between operand stores and MMAs (2.19 ms vs 2.29 ms with the mbarrier hand-off)
   // TMEM columns are held by a CTA for its whole (persistent) lifetime: 512 / columns-per-CTA CTAs may share an SM, one
   // more would sit in tcgen05.alloc until another CTA exits, and the block scheduler knows nothing about TMEM
   // (observed: a 5th CTA with 128 columns landing on an SM turned 2.7 ms into 4.3 ms per launch).  The shared-memory
   // request is therefore padded so that never more CTAs fit than registers and TMEM admit.
-  const int want = single ? 5 : 4;  // two-slot kernel: 128 columns -> 4 CTAs;  single slot: 64 columns, 96 registers -> 5 CTAs
+  const int want = variant == 3 ? blocks8 : (single ? 5 : 4);  // two-slot kernel: 128 columns -> 4 CTAs;  single slot: 64 columns, 96 registers -> 5 CTAs
   // smallest request that keeps a (want+1)-th CTA out (anything larger only shrinks the L1 cache: 44 KB instead of 38 KB
   // per CTA cost 2.49 -> 3.50 ms per launch of the single-slot kernel)
   const size_t pad = (size_t)(233472 / (want + 1)) - 2048 + 512;
@@ -144,7 +152,10 @@ int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int imag
     return cudaGetLastError();
   };
   cudaError_t e;
-  if (single) e = run(dune_tc_kernel, 128);
+  if (variant == 3) {
+    if (blocks8 == 4) e = fast ? run(dune_tc8_kernel<true, 4>, 256) : run(dune_tc8_kernel<false, 4>, 256);
+    else e = fast ? run(dune_tc8_kernel<true, 3>, 256) : run(dune_tc8_kernel<false, 3>, 256);
+  } else if (single) e = run(dune_tc_kernel, 128);
   else if (barrier_sync) e = fast ? run(dune_tcp_kernel<0, true>, 128) : run(dune_tcp_kernel<0, false>, 128);
   else e = fast ? run(dune_tcp_kernel<1, true>, 128) : run(dune_tcp_kernel<1, false>, 128);
   if (e != cudaSuccess) {

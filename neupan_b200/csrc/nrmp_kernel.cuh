@@ -54,9 +54,10 @@ struct NrmpParams {
   // warm start (NB_OPT_NRMP_WARM): per-env float record [x (2T) | D (T) | z of the box/rate/D rows (mb) | z of the hinge rows (T*M)]
   // of the last converged solve; warm_valid[b] != 0 marks it usable.  nullptr = always cold.
   float* warm; int32_t* warm_valid;
+  int* work_counter;  // dynamic env -> warp assignment (see nrmp_kernel), or nullptr
   int B, T, M, E, kin;
   int max_ipm_iter;
-  double gap_tol;  // mean complementarity at termination (1e-13: the one-row hinge form needs it for 1e-7 accuracy in u)
+  double gap_tol;  // mean complementarity at termination (1e-12; the one-row hinge form has no degenerate pairs that would dominate the mean, so the same accuracy in u needs a smaller number than the 1e-10 of the two-row form)
   float iter_threshold;
   double dt, L;
   float q[3], p_u, eta, d_max, d_min;
@@ -148,33 +149,15 @@ __device__ __forceinline__ float rcpf(double x) {
 // 29 KB of shared memory per CTA.  At B = 4096 that is 2072 resident solves = two full rounds instead of 2.3 rounds of
 // 1776; measured 1.39 -> 1.25 ms per launch.  (__maxnreg__(144) instead of the min-blocks bound spills more and is slower.)
 template <int HPL, bool SMALL, int TT, int MM>
-__global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6 : 4)) nrmp_kernel(const NrmpParams prm, int warps_per_cta, int warp_doubles_rt) {
-  extern __shared__ __align__(16) double smem_d[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int b, double* wsp, const unsigned short* __restrict__ ptab, const int lane) {
   const int T = TT > 0 ? TT : prm.T, M = TT > 0 ? MM : prm.M, T1 = T + 1;
-  const int warp_doubles = TT > 0 ? (int)nrmp_warp_doubles(TT, MM) : warp_doubles_rt;
   const int nU = 2 * T, nR = nU - 2, TD = M > 0 ? T : 0, TM = T * M;
   const int nP = nU * (nU + 1) / 2;
   const int oBU = 0, oBL = nU, oRU = 2 * nU, oRL = oRU + nR, oDU = oRL + nR, oDL = oDU + TD;
   const int mb = oDL + TD;
   auto hrow = [](int i) { return (i * (i + 3)) >> 1; };  // offset of row i of the lower-triangular H / L
 
-  // pair table (i << 8 | j) of the lower triangle, shared by the CTA
-  unsigned short* ptab = reinterpret_cast<unsigned short*>(smem_d + (size_t)warps_per_cta * warp_doubles);
-  for (int p = threadIdx.x; p < nP; p += blockDim.x) {
-    int i = (int)((sqrtf(8.0f * p + 1.0f) - 1.0f) * 0.5f);
-    while (i * (i + 1) / 2 > p) --i;
-    while ((i + 1) * (i + 2) / 2 <= p) ++i;
-    ptab[p] = (unsigned short)((i << 8) | (p - i * (i + 1) / 2));
-  }
-  __syncthreads();
-
-  const int b = blockIdx.x * warps_per_cta + warp;
-  if (b >= prm.B) return;
-  if (prm.active && prm.active[b] == 0) return;
-
   // ---- carve this warp's workspace -------------------------------------------------------
-  double* wsp = smem_d + (size_t)warp * warp_doubles;
   const int FT = T * (T + 1);                      // packed size of one component of F / G
   double* F = wsp;            wsp += 3 * FT;       // F[r][t][j] at r*FT + t(t+1) + j, j < 2(t+1)  (zero beyond)
   double* s0 = wsp;           wsp += 3 * T;        // s0[r][t]
@@ -351,6 +334,20 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
     }
   }
 
+  // gradient scale of the program: the dual-residual test is relative to it.  An environment whose cost gradient is O(1e3)
+  // cannot reach an absolute 1e-8 in FP64 once the barrier weights are large; its residual then idles at ~2e-8 while the gap is
+  // driven to 1e-16 and the factorisation finally breaks (seen on 5 % of the C5 problems and on C4 env 934 in the CPU oracle).
+  double res_scale = 1.0;
+  {
+    double m = 0.0;
+    NB_LL(i, nU) m = fmax(m, fabs(cv[i]));
+#pragma unroll
+    for (int q_ = 0; q_ < HPL; ++q_)
+      if (lane + 32 * q_ < TM) m = fmax(m, rho * fabs(hkk[q_]));
+    res_scale = fmax(1.0, warp_max(m));
+  }
+  const double res_tol = 1e-8 * res_scale;
+
   // ---- 5. strictly feasible start: cold (u = 0, D mid-range) or warm (previous solve of this environment) ------
   int stat = 0;
   if (TD > 0 && dhi < dlo) stat |= 4;
@@ -360,9 +357,19 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
   }
   const size_t warm_floats = nrmp_warm_floats(T, M);
   float* wrec = prm.warm ? prm.warm + (size_t)b * warm_floats : nullptr;
-  const bool warm = wrec != nullptr && prm.warm_valid[b] != 0 && stat == 0;
+  const bool try_warm = wrec != nullptr && prm.warm_valid[b] == 1 && stat == 0;
   const double dmid = 0.5 * (dlo + dhi);
-  constexpr double kTheta = 0.05, kMu0 = 1e-2, kDw = 0.03;  // measured on C4 / C2 problem sequences: DESIGN.md 3.2
+  // warm start constants, measured on C4 / C2 problem sequences: pull-back towards the centre, complementarity
+  // floor mu0, cap kKappa * mu0 on s z (an uncapped multiplier of a row that is no longer active leaves Mehrotra's iteration in
+  // a 2-cycle: C4 envs 1507 / 2530), margin of the hinge rows
+  constexpr double kTheta = 0.05, kMu0 = 1e-2, kDw = 0.03, kKappa = 100.0;
+  int it = 0, it_total = 0;
+  bool converged = false, banned = false;
+#pragma unroll 1
+  for (int attempt = 0; attempt < 2; ++attempt) {  // attempt 0: warm if allowed; attempt 1: cold restart of a warm start that went wrong
+  const bool warm = try_warm && attempt == 0;
+  bool restart = false;
+  stat &= ~3;
   NB_LL(i, nU) x[i] = warm ? (1.0 - kTheta) * (double)wrec[i] : 0.0;
   NB_LL(t, TD) Dv[t] = dfix ? dlo : (warm ? (1.0 - kTheta) * (double)wrec[nU + t] + kTheta * dmid : dmid);
   __syncwarp();
@@ -372,14 +379,18 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
     const double su = en_speed[c] ? prm.speed[c] - xi : 1.0, sl = en_speed[c] ? prm.speed[c] + xi : 1.0;
     cs[oBU + i] = su; cs[oBL + i] = sl;
     double zu = en_speed[c] ? (warm ? kMu0 : 1.0) / su : 0.0, zl = en_speed[c] ? (warm ? kMu0 : 1.0) / sl : 0.0;
-    if (warm && en_speed[c]) { zu = fmax(zu, (double)wrec[nU + TD + oBU + i]); zl = fmax(zl, (double)wrec[nU + TD + oBL + i]); }
+    if (warm && en_speed[c]) {
+      zu = fmin(fmax(zu, (double)wrec[nU + TD + oBU + i]), kKappa * zu); zl = fmin(fmax(zl, (double)wrec[nU + TD + oBL + i]), kKappa * zl);
+    }
     cz[oBU + i] = zu; cz[oBL + i] = zl;
     if (i < nR) {
       const double dd = x[i + 2] - xi;
       const double ru = en_acce[c] ? prm.acce[c] - dd : 1.0, rl = en_acce[c] ? prm.acce[c] + dd : 1.0;
       cs[oRU + i] = ru; cs[oRL + i] = rl;
       double yu = en_acce[c] ? (warm ? kMu0 : 1.0) / ru : 0.0, yl = en_acce[c] ? (warm ? kMu0 : 1.0) / rl : 0.0;
-      if (warm && en_acce[c]) { yu = fmax(yu, (double)wrec[nU + TD + oRU + i]); yl = fmax(yl, (double)wrec[nU + TD + oRL + i]); }
+      if (warm && en_acce[c]) {
+        yu = fmin(fmax(yu, (double)wrec[nU + TD + oRU + i]), kKappa * yu); yl = fmin(fmax(yl, (double)wrec[nU + TD + oRL + i]), kKappa * yl);
+      }
       cz[oRU + i] = yu; cz[oRL + i] = yl;
     }
   }
@@ -390,7 +401,7 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
       const double su = dhi - Dv[t], sl = Dv[t] - dlo;
       cs[oDU + t] = su; cs[oDL + t] = sl;
       double zu = (warm ? kMu0 : 1.0) / su, zl = (warm ? kMu0 : 1.0) / sl;
-      if (warm) { zu = fmax(zu, (double)wrec[nU + TD + oDU + t]); zl = fmax(zl, (double)wrec[nU + TD + oDL + t]); }
+      if (warm) { zu = fmin(fmax(zu, (double)wrec[nU + TD + oDU + t]), kKappa * zu); zl = fmin(fmax(zl, (double)wrec[nU + TD + oDL + t]), kKappa * zl); }
       cz[oDU + t] = zu; cz[oDL + t] = zl;
     }
     // position offset F x of the start (zero when cold): qx / qy are free until the first Newton solve
@@ -411,7 +422,10 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
       const double r = Dv[t] + hkk[q_] - ((double)hfx[q_] * qx[t] + (double)hfy[q_] * qy[t]);
       // s = z/rho - r > 0 needs z > rho r; rows far on the inactive side may start with a small multiplier
       double z;
-      if (warm) z = fmax(fmax((double)wrec[nU + TD + mb + k], rho * fmax(r + kDw, 0.0)), kMu0 / fmax(-r, kDw));
+      if (warm) {
+        const double zlo = fmax(rho * fmax(r + kDw, 0.0), kMu0 / fmax(-r, kDw));
+        z = fmax(fmin((double)wrec[nU + TD + mb + k], fmax(kKappa * kMu0 / fmax(-r, kDw), zlo)), zlo);
+      }
       else z = fmax(rho * fmax(r + 0.1, 0.0), 1.0 / fmax(-r, 0.1));
       hz[q_] = z; hs[q_] = z / rho - r;
     }
@@ -419,8 +433,8 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
   __syncwarp();
 
   // ---- 6. interior point iterations -------------------------------------------------------------
-  int it = 0;
-  bool converged = false;
+  converged = false;
+  bool accept_gap = false;
   if (stat == 0) {
 #pragma unroll 1
     for (it = 0; it < prm.max_ipm_iter; ++it) {
@@ -477,7 +491,11 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
       res = warp_max(res);
       const double gap = warp_sum(gsum) * inv_m;
       if (!(gap == gap) || !(res == res)) { stat |= 2; break; }
-      if (gap < prm.gap_tol && res < 1e-8) { converged = true; break; }
+      if (gap < prm.gap_tol && res < res_tol) { converged = true; break; }
+      // a warm start that is not well on its way by iteration 12 (gap still above 1e-5; a healthy one is below 1e-8 there) is
+      // abandoned for a cold start -- rare (<1 % on C4), but one 60-iteration straggler would set the duration of the launch
+      if (warm && it == 12 && gap > 1e-5) { restart = true; break; }
+      accept_gap = gap < 1e-9 && res < 10.0 * res_tol;  // good enough to keep if the next factorisation fails in rounding noise
 
       // (b) barrier weights; hinge rows publish omega for the per-step reductions
       __syncwarp();
@@ -611,7 +629,11 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
           __syncwarp();
         }
       }
-      if (bad) { stat |= 2; break; }
+      if (bad) {  // H lost definiteness: at barrier weights of 1e13+ that is rounding, and the iterate is already the optimum
+        if (accept_gap) converged = true;
+        else stat |= 2;
+        break;
+      }
 
       // (e) predictor (pass 0) and corrector (pass 1) share one Newton body
       NB_LL(k, mb) cdz[k] = enabled(k) ? -cs[k] * cz[k] : 0.0;
@@ -777,8 +799,13 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
       }
       __syncwarp();
     }
-    if (!converged && !(stat & 2)) stat |= 1;
+    if (!converged && !(stat & 2) && !restart) stat |= 1;
   }
+  it_total += it;
+  if (warm && (restart || (stat & 3))) { banned = true; continue; }  // cold restart
+  break;
+  }  // attempt
+  it = it_total;
   if (wrec) {  // the next PAN iteration of this environment starts from here (only from a converged solve)
     __syncwarp();
     if (stat == 0) {
@@ -789,7 +816,8 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
       for (int q_ = 0; q_ < HPL; ++q_)
         if (lane + 32 * q_ < TM) wrec[nU + TD + mb + lane + 32 * q_] = (float)hz[q_];
     }
-    if (lane == 0) prm.warm_valid[b] = stat == 0 ? 1 : 0;
+    // 2 = this environment's warm start failed once in this forward(): its remaining solves start cold
+    if (lane == 0) prm.warm_valid[b] = stat == 0 ? (banned || prm.warm_valid[b] == 2 ? 2 : 1) : 0;
   }
 
   // ---- 7. outputs: S = s0 + F u, U, D cast to float32 (nrmp.py:145-148) --------------------------
@@ -874,6 +902,45 @@ __global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6
       prm.prev_count[b] = cur_cnt;
       if (valid && diff < prm.iter_threshold && prm.active) prm.active[b] = 0;
     }
+  }
+}
+
+// Kernel: persistent warps.  Every warp owns one workspace in shared memory and pulls environments from a global counter
+// (prm.work_counter, zeroed by the launcher) until the batch is exhausted: solves take 8..25 interior point iterations, so
+// a static env -> warp map leaves the fast warps of a wave idle (and a CTA slot is only re-used when BOTH its warps are done).
+// work_counter == nullptr: one environment per warp (b = blockIdx.x * warps + warp), the grid covers the batch.
+template <int HPL, bool SMALL, int TT, int MM>
+__global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6 : 4)) nrmp_kernel(const NrmpParams prm, int warps_per_cta, int warp_doubles_rt) {
+  extern __shared__ __align__(16) double smem_d[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int T = TT > 0 ? TT : prm.T, M = TT > 0 ? MM : prm.M;
+  const int warp_doubles = TT > 0 ? (int)nrmp_warp_doubles(TT, MM) : warp_doubles_rt;
+  const int nU = 2 * T, nP = nU * (nU + 1) / 2;
+  (void)M;
+  // pair table (i << 8 | j) of the lower triangle, shared by the CTA
+  unsigned short* ptab = reinterpret_cast<unsigned short*>(smem_d + (size_t)warps_per_cta * warp_doubles);
+  for (int p = threadIdx.x; p < nP; p += blockDim.x) {
+    int i = (int)((sqrtf(8.0f * p + 1.0f) - 1.0f) * 0.5f);
+    while (i * (i + 1) / 2 > p) --i;
+    while ((i + 1) * (i + 2) / 2 <= p) ++i;
+    ptab[p] = (unsigned short)((i << 8) | (p - i * (i + 1) / 2));
+  }
+  __syncthreads();
+  double* wsp = smem_d + (size_t)warp * warp_doubles;
+  if (prm.work_counter == nullptr) {
+    const int b = blockIdx.x * warps_per_cta + warp;
+    if (b < prm.B && !(prm.active && prm.active[b] == 0)) nrmp_solve_env<HPL, SMALL, TT, MM>(prm, b, wsp, ptab, lane);
+    return;
+  }
+#pragma unroll 1
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(prm.work_counter, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= prm.B) break;
+    if (prm.active && prm.active[b] == 0) continue;
+    nrmp_solve_env<HPL, SMALL, TT, MM>(prm, b, wsp, ptab, lane);
+    __syncwarp();
   }
 }
 

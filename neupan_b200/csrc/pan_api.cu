@@ -24,7 +24,8 @@ int launch_dune_mma(const DuneParams& prm, const unsigned char* d_image, int sm_
                     char* err, size_t errlen);
 // dune_tc.cu
 int build_tc_image(const float* w, int E, std::vector<unsigned char>& out);
-int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int image_flags, int sm_count, int max_smem_optin, cudaStream_t st, char* err, size_t errlen);
+int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int image_flags, int variant, int sm_count, int max_smem_optin, cudaStream_t st, char* err,
+                   size_t errlen);
 }  // namespace nb
 
 namespace {
@@ -85,10 +86,12 @@ struct nb_pan {
   float *prev_s = nullptr, *prev_u = nullptr, *prev_mu = nullptr, *prev_lam = nullptr;
   int32_t *prev_count = nullptr, *prev_valid = nullptr, *active = nullptr, *iters = nullptr, *status = nullptr, *ipm_it = nullptr;
   float* min_dist = nullptr;
+  int* work_counters = nullptr;     // dynamic env -> warp assignment of the NRMP kernel, one counter per internal stream
+  int nrmp_dynamic = 1;             // NB_NRMP_STATIC=1 (developer switch, read at create) turns the persistent-warp schedule off
   float* warm = nullptr;            // NRMP warm-start records, nrmp_warm_floats(T, M) per environment
   int32_t* warm_valid = nullptr;
-  int nrmp_warm = 1;                // NB_OPT_NRMP_WARM
-  double nrmp_gap_tol = 1e-13;      // NB_NRMP_GAP_TOL (developer switch, read once at create)
+  int nrmp_warm = 0;                // NB_OPT_NRMP_WARM (off by default: see DESIGN.md 3.2)
+  double nrmp_gap_tol = 1e-12;      // NB_NRMP_GAP_TOL (developer switch, read once at create)
   // staging for the host-pointer entry point
   float *h_in = nullptr, *h_out = nullptr;  // device staging
   size_t h_in_floats = 0, h_out_floats = 0;
@@ -116,8 +119,8 @@ int check_forward_args(const nb_pan* p, int B, int N) {
 int launch_dune(nb_pan* p, const nb::DuneParams& prm, cudaStream_t st, int cta_limit = 0) {
   int rc = NB_ERR_INVALID;
   char msg[256] = "";
-  if (p->dune_variant == 2) {
-    rc = nb::launch_dune_tc(prm, p->d_tc_image, p->tc_flags, p->sm_count, p->max_smem_optin, st, msg, sizeof(msg));
+  if (p->dune_variant >= 2) {
+    rc = nb::launch_dune_tc(prm, p->d_tc_image, p->tc_flags, p->dune_variant, p->sm_count, p->max_smem_optin, st, msg, sizeof(msg));
     if (rc) return fail(rc, "%s", msg);
     ++g_launches;
     return NB_OK;
@@ -160,7 +163,7 @@ int launch_dune(nb_pan* p, const nb::DuneParams& prm, cudaStream_t st, int cta_l
   return NB_OK;
 }
 
-int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st) {
+int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st, int counter_slot = 0) {
   const nb_pan_config& c = p->cfg;
   prm.T = c.receding; prm.M = c.nrmp_max_num; prm.E = c.edge_dim; prm.kin = c.kinematics;
   prm.max_ipm_iter = 60;
@@ -184,9 +187,20 @@ int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st) {
   // small CTAs (<= 2 warps): many of them fit per SM and each warp retires independently
   if (warps > 2) warps = 2;
   const size_t smem = (size_t)warps * wd * sizeof(double) + extra;
-  const int grid = (prm.B + warps - 1) / warps;
+  int grid = (prm.B + warps - 1) / warps;
   auto go = [&](auto kern) -> int {
     NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem_optin));
+    if (p->nrmp_dynamic && p->work_counters) {
+      // persistent warps: as many CTAs as are resident at once; they pull environments from a counter until the batch is done
+      int per_sm = 0;
+      NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+      const int resident = (per_sm > 0 ? per_sm : 1) * p->sm_count;
+      if (grid > resident) {
+        grid = resident;
+        prm.work_counter = p->work_counters + counter_slot;
+        NB_CUDA(cudaMemsetAsync(prm.work_counter, 0, sizeof(int), st));
+      }
+    }
     kern<<<grid, warps * 32, smem, st>>>(prm, warps, (int)wd);
     ++g_launches;
     NB_CUDA(cudaGetLastError());
@@ -301,6 +315,8 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
   NB_CUDA(dalloc(&p->min_dist, B));
   NB_CUDA(dalloc(&p->warm, B * nb::nrmp_warm_floats(cfg->receding, cfg->nrmp_max_num)));
   NB_CUDA(dalloc(&p->warm_valid, B));
+  NB_CUDA(dalloc(&p->work_counters, (size_t)8));
+  if (getenv("NB_NRMP_STATIC")) p->nrmp_dynamic = 0;
   NB_CUDA(cudaMemset(p->warm_valid, 0, B * sizeof(int32_t)));
   if (const char* e = getenv("NB_NRMP_GAP_TOL")) p->nrmp_gap_tol = atof(e);
   NB_CUDA(cudaMemset(p->prev_valid, 0, B * sizeof(int32_t)));
@@ -320,7 +336,7 @@ int nb_pan_destroy(nb_pan_t* p) {
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   void* bufs[] = {p->d_tc_image, p->d_image, p->d_weights, p->sel_mu, p->sel_lam, p->sel_pts, p->sel_dist, p->sel_count, p->prev_s, p->prev_u, p->prev_mu,
                   p->prev_lam, p->prev_count, p->prev_valid, p->active, p->iters, p->status, p->ipm_it, p->min_dist, p->h_in, p->h_out, p->h_np, p->h_io,
-                  p->warm, p->warm_valid};
+                  p->warm, p->warm_valid, p->work_counters};
   for (void* b : bufs)
     if (b) cudaFree(b);
   delete p;
@@ -343,7 +359,7 @@ int nb_pan_set_iteration(nb_pan_t* p, int32_t iter_num, float iter_threshold) {
 int nb_pan_set_option(nb_pan_t* p, int32_t option, int32_t value) {
   if (!p) return fail(NB_ERR_INVALID, "null handle");
   if (option == NB_OPT_DUNE_KERNEL) {
-    if (value < 0 || value > 2) return fail(NB_ERR_INVALID, "NB_OPT_DUNE_KERNEL takes 0 (fp32 ffma), 1 (mma.sync) or 2 (tcgen05)");
+    if (value < 0 || value > 3) return fail(NB_ERR_INVALID, "NB_OPT_DUNE_KERNEL takes 0 (fp32 ffma), 1 (mma.sync), 2 (tcgen05, thread per point) or 3 (tcgen05, two threads per point)");
     p->dune_variant = value;
     return NB_OK;
   }
@@ -428,7 +444,7 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
   NB_CUDA(cudaMemcpyAsync(out_u, nom_u, (size_t)B * 2 * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
   NB_CUDA(cudaMemsetAsync(out_d, 0, (size_t)B * T * sizeof(float), st));
   // K iterations of {DUNE, NRMP} for the environments [lo, hi) on stream s
-  auto run_range = [&](int lo, int hi, cudaStream_t s, int dune_cta_limit) -> int {
+  auto run_range = [&](int lo, int hi, cudaStream_t s, int dune_cta_limit, int counter_slot) -> int {
     const int nb_ = hi - lo;
     const size_t T1s = (size_t)T1, Ms = (size_t)c.nrmp_max_num, Es = (size_t)(c.edge_dim > 0 ? c.edge_dim : 1);
     for (int k = 0; k < c.iter_num; ++k) {
@@ -460,13 +476,13 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
         n.warm_valid = p->warm_valid + lo;
       }
       n.B = nb_;
-      if (int rc = launch_nrmp(p, n, s)) return rc;
+      if (int rc = launch_nrmp(p, n, s, counter_slot)) return rc;
     }
     return NB_OK;
   };
   const int parts = (p->overlap > 1 && with_dune && B >= 64 * p->overlap) ? p->overlap : 1;
   if (parts == 1) {
-    if (int rc = run_range(0, B, st, 0)) return rc;
+    if (int rc = run_range(0, B, st, 0, 0)) return rc;
   } else {
     // sub-batches on internal streams: the DUNE kernel of one part (issue / tensor / MUFU bound) shares the SMs with the
     // NRMP kernel of another (latency bound, few warps)
@@ -474,7 +490,7 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
     for (int i = 0; i < parts; ++i) {
       NB_CUDA(cudaStreamWaitEvent(p->streams[i], p->ev_fork, 0));
       const int lo = (int)((long long)B * i / parts), hi = (int)((long long)B * (i + 1) / parts);
-      if (int rc = run_range(lo, hi, p->streams[i], 1)) return rc;
+      if (int rc = run_range(lo, hi, p->streams[i], 1, 1 + i)) return rc;
       NB_CUDA(cudaEventRecord(p->ev_join[i], p->streams[i]));
       NB_CUDA(cudaStreamWaitEvent(st, p->ev_join[i], 0));
     }
