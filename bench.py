@@ -253,7 +253,8 @@ class PanBench:
 
     def step(self, i, host=False):
         d = (self.hsets if host else self.dsets)[i % self.n_sets]
-        return self.sp.step(d["nom_s"], d["nom_u"], d["ref_s"], d["ref_us"], d["points"], d["velocities"])
+        with self.torch.no_grad():  # inference (with autograd recording PAN.forward runs in differentiable mode, like cvxpylayers would)
+            return self.sp.step(d["nom_s"], d["nom_u"], d["ref_s"], d["ref_us"], d["points"], d["velocities"])
 
     def barrier(self):
         import torch.distributed as dist

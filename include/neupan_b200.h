@@ -119,9 +119,24 @@ int nb_pan_set_iteration(nb_pan_t* pan, int32_t iter_num, float iter_threshold);
  * of one sub-batch shares the SMs with the NRMP kernel of another (results are identical; envs are independent).
  * NB_OPT_NRMP_WARM: 1 = inside one nb_pan_forward the NRMP solve of PAN iteration k > 0 starts from the solution of
  * iteration k-1 of the same environment (fewer interior point iterations on average, same optimum to the solver tolerance;
- * a warm start that is not converging by its 12th iteration is abandoned for a cold one); 0 (default) = every solve starts cold.  The first solve of every call is always cold, so results never depend on earlier calls. */
-enum { NB_OPT_DUNE_KERNEL = 1, NB_OPT_OVERLAP = 2, NB_OPT_NRMP_WARM = 3 };
+ * a warm start that is not converging by its 12th iteration is abandoned for a cold one); 0 (default) = every solve starts
+ * cold.  The first solve of every call is always cold, so results never depend on earlier calls.
+ * NB_OPT_DUNE_KERNEL also takes 3 = tcgen05 with two threads per point (8 warps per 128-point tile; measured slower, kept for A/B).
+ * NB_OPT_DIFFERENTIABLE: 1 = every NRMP solve of nb_pan_forward also stores what nb_pan_backward needs (one extra factorisation
+ * at the optimum + ~5 KB per environment and iteration); 0 (default) = inference only. */
+enum { NB_OPT_DUNE_KERNEL = 1, NB_OPT_OVERLAP = 2, NB_OPT_NRMP_WARM = 3, NB_OPT_DIFFERENTIABLE = 4 };
 int nb_pan_set_option(nb_pan_t* pan, int32_t option, int32_t value);
+
+/* Replaces the backward pass of the reference's differentiable solve (CvxpyLayer, nrmp.py:144; used by LON,
+ * example/LON/LON_corridor.py:94 `loss.backward()`): given dL/d(out_s) (B,3,T+1), dL/d(out_u) (B,2,T), dL/d(out_d) (B,T) of the
+ * LAST nb_pan_forward (made with NB_OPT_DIFFERENTIABLE = 1; any gradient pointer may be NULL = zeros) it writes
+ * grad_theta (B,7) = dL/d(q_s[0], q_s[1], q_s[2], p_u, eta, d_max, d_min) per environment (a scalar q_s is the sum of the
+ * first three; parameters shared by the batch are the sum over environments).  Like the reference, the gradient flows through
+ * every PAN iteration's solve: directly through the adjust parameters (incl. gamma_a = q_s ref_s, gamma_b = p_u ref_us,
+ * nrmp.py:156-159) and from iteration k to k-1 through `nom_s` (the proximal term and nothing else: A, B, C, fa, fb are rebuilt
+ * from detached values in the reference, robot.py:272-316, dune.py:78-95).  ref_s / ref_us are the tensors of the forward call. */
+int nb_pan_backward(nb_pan_t* pan, int32_t B, const float* ref_s, const float* ref_us,
+                    const float* grad_s, const float* grad_u, const float* grad_d, float* grad_theta, void* stream);
 
 /* Forget PAN.current_nom_values (pan.py:100-105) of all environments.  (The reference's
  * neupan.reset() does NOT do this, neupan/neupan.py:288-294; exposed for tests and for

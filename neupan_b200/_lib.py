@@ -20,6 +20,7 @@ STATUS_MAXITER, STATUS_NUMERIC, STATUS_INFEASIBLE = 1, 2, 4
 OPT_DUNE_KERNEL = 1
 OPT_OVERLAP = 2
 OPT_NRMP_WARM = 3
+OPT_DIFFERENTIABLE = 4
 
 
 class PanConfig(C.Structure):
@@ -66,6 +67,7 @@ SYMBOLS = {
     "nb_pan_set_option": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "nb_pan_reset_state": (C.c_int, [C.c_void_p]),
     "nb_pan_reset_state_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nb_pan_backward": (C.c_int, [C.c_void_p, C.c_int32] + [_FP] * 6 + [C.c_void_p]),
     "nb_pan_read_selection": (C.c_int, [C.c_void_p, C.c_int32] + [_FP] * 5 + [C.c_void_p]),
     "nb_pan_read_diagnostics": (C.c_int, [C.c_void_p, C.c_int32, _FP, C.c_void_p]),
     "nb_dune_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [_FP] * 5 + [C.c_void_p]),

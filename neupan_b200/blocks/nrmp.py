@@ -1,9 +1,11 @@
 """NRMP layer facade (mirrors neupan/blocks/nrmp.py:33-392).
 
-Keeps the reference's adjustable parameters (q_s, p_u, eta, d_max, d_min as tensors,
-``adjust_parameters`` list, ``update_adjust_parameters_value``) and ``points``.  The convex
-program the reference builds with cvxpy (nrmp.py:263-383) is solved by the CUDA NRMP kernel
-(neupan_b200/csrc/nrmp_kernel.cuh); there is no cvxpy / cvxpylayers dependency.
+Keeps the reference's adjustable parameters (q_s, p_u, eta, d_max, d_min as leaf tensors with
+``requires_grad=True``, ``adjust_parameters`` list, ``update_adjust_parameters_value``) and ``points``.  The
+convex program the reference builds with cvxpy (nrmp.py:263-383) is solved by the CUDA NRMP kernel
+(neupan_b200/csrc/nrmp_kernel.cuh); there is no cvxpy / cvxpylayers dependency.  When autograd is recording,
+``PAN.forward`` runs the native solve in differentiable mode and ``loss.backward()`` reaches these leaves through
+``nb_pan_backward`` (adjoint solves on the device) -- the role of CvxpyLayer's backward in the reference (LON).
 """
 from __future__ import annotations
 

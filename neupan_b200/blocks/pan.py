@@ -33,6 +33,43 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+class _PanSolve(torch.autograd.Function):
+    """Differentiable PAN.forward: the forward is the native nb_pan_forward in differentiable mode, the backward is
+    nb_pan_backward (adjoint solves of the K NRMP programs on the device) -- what CvxpyLayer's backward does in the reference
+    (nrmp.py:144), reaching the leaves q_s, p_u, eta, d_max, d_min of NRMP.adjust_parameters (nrmp.py:79-104)."""
+
+    @staticmethod
+    def forward(ctx, pan, run, ref_s, ref_us, q_s, p_u, *dist_params):
+        out_s, out_u, out_d = run()
+        ctx.pan, ctx.ref_s, ctx.ref_us = pan, ref_s, ref_us
+        ctx.q_shape, ctx.n_dist = tuple(q_s.shape), len(dist_params)
+        ctx.out_device = out_s.device
+        ctx.forward_id = pan._forward_id
+        return out_s, out_u, out_d
+
+    @staticmethod
+    def backward(ctx, g_s, g_u, g_d):
+        pan = ctx.pan
+        if pan._forward_id != ctx.forward_id:
+            raise RuntimeError("neupan_b200.PAN: backward() of an earlier forward -- the native adjoint records belong to the latest forward only "
+                               "(call loss.backward() before the next planner step, as example/LON does)")
+        dev = pan.device
+        B = ctx.ref_s.shape[0]
+        prep = lambda t: None if t is None else t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        g_s, g_u = prep(g_s), prep(g_u)
+        g_d = None if g_d is None else prep(g_d).reshape(B, -1)
+        ref_s, ref_us = prep(ctx.ref_s), prep(ctx.ref_us)
+        gth = torch.empty((B, 7), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(_lib.load().nb_pan_backward(pan._handle, B, _ptr(ref_s), _ptr(ref_us), _ptr(g_s), _ptr(g_u), _ptr(g_d), _ptr(gth), stream))
+        pan.last_grad_theta = gth  # (B, 7) per-environment gradients [q0, q1, q2, p_u, eta, d_max, d_min] (diagnostics / tests)
+        g = gth.sum(0).to("cpu")  # the adjust parameters are shared by the batch
+        gq = g[0:3].reshape(3, 1) if ctx.q_shape == (3, 1) else g[0:3].sum().reshape(ctx.q_shape)
+        grads = [gq, g[3].reshape(()), g[4].reshape(()), g[5].reshape(()), g[6].reshape(())]
+        return (None, None, None, None, *grads[:2 + ctx.n_dist])
+
+
 class PAN(torch.nn.Module):
     def __init__(self, receding=10, step_time=0.1, robot=None, iter_num=2, dune_max_num=100, nrmp_max_num=10, dune_checkpoint=None,
                  iter_threshold=0.1, adjust_kwargs=None, train_kwargs=None, **kwargs) -> None:
@@ -67,6 +104,8 @@ class PAN(torch.nn.Module):
         self.nrmp_warm = int(kwargs.get("nrmp_warm", 0))  # 1 = NRMP solves of PAN iterations k > 0 start from iteration k-1's solution (fewer IPM iterations on average, but stragglers: DESIGN.md 3.2)
         self.dune_kernel = int(kwargs.get("dune_kernel", 2))  # 2 = tcgen05 DUNE kernel (default), 1 = mma.sync, 0 = all-FP32 FFMA
         self._cap = (max(1, int(kwargs.get("max_envs", 1))), max(1, int(kwargs.get("max_points", max(1, dune_max_num)))))
+        self._forward_id = 0
+        self._differentiable = None  # last NB_OPT_DIFFERENTIABLE value pushed to the handle
         self._sent = None  # (adjust version, iter_num, iter_threshold) last pushed to the handle
         self._last = None  # bookkeeping of the last forward (for the lazy properties)
 
@@ -141,6 +180,7 @@ class PAN(torch.nn.Module):
         if self._handle is not None:
             _lib.load().nb_pan_destroy(self._handle)
             self._handle = None
+            self._differentiable = None
 
     def __del__(self):
         try:
@@ -203,13 +243,28 @@ class PAN(torch.nn.Module):
         if num_points is not None:
             num_points = num_points.detach().to(device=io_dev, dtype=torch.int32).contiguous()
         mk = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype, device=io_dev, pin_memory=host and torch.cuda.is_available())
-        out_s, out_u, out_d = mk(B, 3, T + 1), mk(B, 2, T), mk(B, T)
         out_md, out_it, out_st = mk(B), mk(B, dtype=torch.int32), mk(B, dtype=torch.int32)
-        with torch.cuda.device(self.device):
-            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            fn = lib.nb_pan_forward_host if host else lib.nb_pan_forward
-            _lib.check(fn(self._handle, B, N, _ptr(nom_s), _ptr(nom_u), _ptr(ref_s), _ptr(ref_us), _ptr(obs_points), _ptr(point_velocities),
-                          _ptr(num_points), _ptr(out_s), _ptr(out_u), _ptr(out_d), _ptr(out_md), _ptr(out_it), _ptr(out_st), stream))
+        # differentiable mode (LON): any adjust parameter that requires grad while autograd is recording
+        leaves = self.nrmp_layer.adjust_parameters
+        want_grad = torch.is_grad_enabled() and any(t.requires_grad for t in leaves)
+        if want_grad != self._differentiable:
+            _lib.check(lib.nb_pan_set_option(self._handle, _lib.OPT_DIFFERENTIABLE, int(want_grad)))
+            self._differentiable = want_grad
+        self._forward_id += 1
+
+        def run():
+            out_s, out_u, out_d = mk(B, 3, T + 1), mk(B, 2, T), mk(B, T)
+            with torch.cuda.device(self.device):
+                stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+                fn = lib.nb_pan_forward_host if host else lib.nb_pan_forward
+                _lib.check(fn(self._handle, B, N, _ptr(nom_s), _ptr(nom_u), _ptr(ref_s), _ptr(ref_us), _ptr(obs_points), _ptr(point_velocities),
+                              _ptr(num_points), _ptr(out_s), _ptr(out_u), _ptr(out_d), _ptr(out_md), _ptr(out_it), _ptr(out_st), stream))
+            return out_s, out_u, out_d
+
+        if want_grad:
+            out_s, out_u, out_d = _PanSolve.apply(self, run, ref_s, ref_us, *leaves)
+        else:
+            out_s, out_u, out_d = run()
         self._last = dict(B=B, N=N, batched=batched, min_distance=out_md, iters=out_it, status=out_st, points=obs_points, use_points=use_points)
         if self.dune_layer is not None:
             if use_points:

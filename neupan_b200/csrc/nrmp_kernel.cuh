@@ -55,6 +55,9 @@ struct NrmpParams {
   // of the last converged solve; warm_valid[b] != 0 marks it usable.  nullptr = always cold.
   float* warm; int32_t* warm_valid;
   int* work_counter;  // dynamic env -> warp assignment (see nrmp_kernel), or nullptr
+  // differentiable mode (LON): per-env record of this solve for nrmp_adjoint_kernel, nrmp_adj_doubles(T, M)
+  // doubles each, and a validity flag; nullptr = inference
+  double* adj_save; int32_t* adj_valid;
   int B, T, M, E, kin;
   int max_ipm_iter;
   double gap_tol;  // mean complementarity at termination (1e-12; the one-row hinge form has no degenerate pairs that would dominate the mean, so the same accuracy in u needs a smaller number than the 1e-10 of the two-row form)
@@ -94,6 +97,14 @@ __host__ __device__ inline size_t nrmp_warp_doubles(int T, int M) {
 __host__ __device__ inline size_t nrmp_cta_extra_bytes(int T) {  // pair table (uint16) shared by the CTA's warps
   const int nU = 2 * T;
   return (((size_t)nU * (nU + 1) / 2) * 2 + 15) / 16 * 16;
+}
+
+// adjoint record of one solve: [L (nU(nU+3)/2) | 1/diag(L) (nU) | F x,y,theta (3 T(T+1)) | 1/H_DD, n0, n1, W_Dmax, W_Dmin (5T) |
+// S rows x,y,theta at t = 1..T (3T) | U0 (T)]
+__host__ __device__ inline size_t nrmp_adj_doubles(int T, int M) {
+  const size_t nU = 2 * (size_t)T;
+  (void)M;
+  return nU * (nU + 3) / 2 + nU + 3 * (size_t)T * (T + 1) + 9 * (size_t)T;
 }
 
 __host__ __device__ inline size_t nrmp_warm_floats(int T, int M) {
@@ -364,7 +375,8 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
   // a 2-cycle: C4 envs 1507 / 2530), margin of the hinge rows
   constexpr double kTheta = 0.05, kMu0 = 1e-2, kDw = 0.03, kKappa = 100.0;
   int it = 0, it_total = 0;
-  bool converged = false, banned = false;
+  bool converged = false, banned = false, have_factor = false;
+  double invd0 = 0.0, invd1 = 0.0;  // 1 / diag(L) of the rows this lane owns (last factorisation)
 #pragma unroll 1
   for (int attempt = 0; attempt < 2; ++attempt) {  // attempt 0: warm if allowed; attempt 1: cold restart of a warm start that went wrong
   const bool warm = try_warm && attempt == 0;
@@ -435,6 +447,7 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
   // ---- 6. interior point iterations -------------------------------------------------------------
   converged = false;
   bool accept_gap = false;
+  have_factor = false;
   if (stat == 0) {
 #pragma unroll 1
     for (it = 0; it < prm.max_ipm_iter; ++it) {
@@ -491,7 +504,10 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
       res = warp_max(res);
       const double gap = warp_sum(gsum) * inv_m;
       if (!(gap == gap) || !(res == res)) { stat |= 2; break; }
-      if (gap < prm.gap_tol && res < res_tol) { converged = true; break; }
+      // differentiable mode: the converged iterate goes through (b)-(d) once more so that the factor that is saved for the
+      // adjoint belongs to the final point
+      const bool finishing = gap < prm.gap_tol && res < res_tol;
+      if (finishing && prm.adj_save == nullptr) { converged = true; break; }
       // a warm start that is not well on its way by iteration 12 (gap still above 1e-5; a healthy one is below 1e-8 there) is
       // abandoned for a cold start -- rare (<1 % on C4), but one 60-iteration straggler would set the duration of the launch
       if (warm && it == 12 && gap > 1e-5) { restart = true; break; }
@@ -499,12 +515,25 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
 
       // (b) barrier weights; hinge rows publish omega for the per-step reductions
       __syncwarp();
-      NB_LL(k, mb) cis[k] = rcpf(cs[k]);
+      // Differentiable mode, final pass: the weights of the factor that is saved for the adjoint come from the central path at
+      // mu_a = 1e-10 instead of the final mu = 1e-12 and are capped at 1e9.  With W = z/s = 1e13+ the information about the cost
+      // Hessian along an active RATE constraint (W (e_{i+2} - e_i)(e_{i+2} - e_i)' couples two controls) survives only through the
+      // cancellation of 1e14-sized entries: measured gradient errors of 1e-2 (C5, acceleration-limited) that grew to 3e-1 with a
+      // tighter gap; a pinned direction held by 1e9 instead of infinity moves the result by 1e-7.
+      //   active row (z >> s):  W = z^2 / mu_a;   inactive (s >> z):  W = mu_a / s^2;   smooth in between
+      NB_LL(k, mb) {
+        if (finishing && enabled(k)) {
+          const double sk = cs[k], zk = cz[k];
+          cis[k] = (float)(fmin((zk * zk + 1e-10) / (sk * sk + 1e-10), 1e9) / zk);
+        } else {
+          cis[k] = rcpf(cs[k]);
+        }
+      }
 #pragma unroll
       for (int q_ = 0; q_ < HPL; ++q_) {
         const int k = lane + 32 * q_;
         if (k < TM) {
-          his[q_] = rcpf(hs[q_]);
+          his[q_] = finishing ? (float)(fmin((hz[q_] * hz[q_] + 1e-10) / (hs[q_] * hs[q_] + 1e-10), 1e9) / hz[q_]) : rcpf(hs[q_]);
           const double Wr = hz[q_] * (double)his[q_];
           hih[q_] = rcp64(rho + Wr);
           tmpk[k] = Wr * rho * hih[q_];  // omega: the row's weight in the reduced Hessian (bounded by rho)
@@ -567,7 +596,7 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
       //     SMALL: two columns per step (nU = 2T is even) -- row i is read once for both dot products, which are two
       //     independent FMA chains; the second column then takes the rank-1 correction of the first.
       bool bad = false;
-      double invd0 = 0.0, invd1 = 0.0;
+      invd0 = 0.0; invd1 = 0.0;
       if (SMALL) {
 #pragma unroll 1
         for (int k = 0; k < nU; k += 2) {
@@ -635,6 +664,7 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
         break;
       }
 
+      if (finishing) { converged = true; have_factor = true; break; }
       // (e) predictor (pass 0) and corrector (pass 1) share one Newton body
       NB_LL(k, mb) cdz[k] = enabled(k) ? -cs[k] * cz[k] : 0.0;
 #pragma unroll
@@ -820,6 +850,31 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
     if (lane == 0) prm.warm_valid[b] = stat == 0 ? (banned || prm.warm_valid[b] == 2 ? 2 : 1) : 0;
   }
 
+  // ---- 6b. differentiable mode: what the adjoint solve of this optimum needs (nrmp_adjoint_kernel) ----------------
+  double* arec = prm.adj_save ? prm.adj_save + (size_t)b * nrmp_adj_doubles(T, M) : nullptr;
+  const bool adj_ok = arec != nullptr && stat == 0 && have_factor;
+  const int oL = 0, oI = (nU * (nU + 3)) >> 1, oF = oI + nU, oP = oF + 3 * FT, oS = oP + 5 * T, oU0 = oS + 3 * T;
+  if (arec) {
+    __syncwarp();
+    if (adj_ok) {
+      NB_LL(i, (nU * (nU + 3)) >> 1) arec[oL + i] = H[i];
+      if (lane < nU) arec[oI + lane] = invd0;
+      if (!SMALL && lane + 32 < nU) arec[oI + lane + 32] = invd1;
+      NB_LL(i, 3 * FT) arec[oF + i] = F[i];
+      NB_LL(t, T) {
+        const bool hasD = TD > 0;
+        arec[oP + t] = hasD ? iHDD[t] : 0.0;
+        arec[oP + T + t] = hasD ? n0[t] : 0.0;
+        arec[oP + 2 * T + t] = hasD ? n1[t] : 0.0;
+        arec[oP + 3 * T + t] = (hasD && !dfix) ? cz[oDU + t] * (double)cis[oDU + t] : 0.0;
+        arec[oP + 4 * T + t] = (hasD && !dfix) ? cz[oDL + t] * (double)cis[oDL + t] : 0.0;
+        arec[oU0 + t] = x[2 * t];
+      }
+    }
+    if (lane == 0) prm.adj_valid[b] = adj_ok ? 1 : 0;
+    __syncwarp();
+  }
+
   // ---- 7. outputs: S = s0 + F u, U, D cast to float32 (nrmp.py:145-148) --------------------------
   float* os = prm.out_s + (size_t)b * 3 * T1;
   float* ou = prm.out_u + (size_t)b * 2 * T;
@@ -833,6 +888,7 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
       sx += F[t * (t + 1) + i] * x[i]; sy += F[FT + t * (t + 1) + i] * x[i]; sth += F[2 * FT + t * (t + 1) + i] * x[i];
     }
     if (keep_nominal) { sx = ns[t + 1]; sy = ns[T1 + t + 1]; sth = ns[2 * T1 + t + 1]; }
+    if (adj_ok) { arec[oS + t] = sx; arec[oS + T + t] = sy; arec[oS + 2 * T + t] = sth; }
     // stash (H is dead) so that every read of nom_s is complete before any write (out may alias nom)
     H[3 * t] = sx; H[3 * t + 1] = sy; H[3 * t + 2] = sth;
   }
@@ -903,6 +959,130 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
       if (valid && diff < prm.iter_threshold && prm.active) prm.active[b] = 0;
     }
   }
+}
+
+// ---- adjoint of one NRMP solve (differentiable mode; replaces the backward pass of CvxpyLayer, nrmp.py:144) -----------------
+// One warp per environment.  With M = P + Ab' W Ab + J' omega J the reduced KKT matrix of the barrier problem at the optimum
+// (its U-block Schur complement is the matrix the forward solve factorised last), dx/dtheta = -M^-1 dF/dtheta, hence
+//   M z = g_x,   g_x = (F' dL/dS + dL/dU, dL/dD);       dL/dtheta_i = -z' dF/dtheta_i
+// with the parameter dependence of the stationarity residual F (gamma_a = q_s ref_s and gamma_b = p_u ref_us included):
+//   dF/dq_r   = 4 q_r sum_t F_t[r]' (S_r - ref_r)_{t+1}      (r < 2 for omni)      dF/dp_u = 4 p_u (U0_t - ref_us_t) e_{u0,t}
+//   dF/deta   = -e_D        dF/dd_max = -W_Dmax e_D        dF/dd_min = -W_Dmin e_D        dF/dpara_s[r,t+1] = -bk F_t[r]'
+// The last one is the gradient that flows on into the previous PAN iteration, whose output S is this solve's `para_s`
+// (pan.py:131-142: nom_s is passed on as a tensor; A, B, C, fa, fb are rebuilt from detached values and carry no gradient).
+struct NrmpAdjParams {
+  const double* rec;         // (B, nrmp_adj_doubles)
+  const int32_t* rec_valid;  // (B)
+  const int32_t* iters;      // (B) iterations executed by the forward; the record is this iteration's iff iters[b] > k
+  int k;
+  const float* ref_s;        // (B,3,T+1)
+  const float* ref_us;       // (B,T)
+  double* g_s;               // (B,3,T+1) upstream dL/dS on entry, dL/dpara_s for the previous iteration on exit
+  double* g_u;               // (B,2,T)   upstream dL/dU on entry, zero on exit
+  double* g_d;               // (B,T)     upstream dL/dD on entry, zero on exit
+  double* grad_theta;        // (B,7) accumulated: q0, q1, q2, p_u, eta, d_max, d_min
+  int B, T, M, kin;
+  float q[3], p_u, d_min;
+  double bk;
+};
+
+__global__ void __launch_bounds__(128) nrmp_adjoint_kernel(const NrmpAdjParams prm) {
+  extern __shared__ __align__(16) double smem_adj[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int b = blockIdx.x * wpc + warp;
+  if (b >= prm.B) return;
+  const int T = prm.T, T1 = T + 1, nU = 2 * T, FT = T * (T + 1);
+  const bool hasD = prm.M > 0;
+  const int nL = (nU * (nU + 3)) >> 1;
+  const int oI = nL, oF = oI + nU, oP = oF + 3 * FT, oS = oP + 5 * T, oU0 = oS + 3 * T;
+  double* gs = prm.g_s + (size_t)b * 3 * T1;
+  double* gu = prm.g_u + (size_t)b * 2 * T;
+  double* gd = prm.g_d + (size_t)b * T;
+  if (prm.iters[b] <= prm.k) return;  // this environment had stopped before iteration k: its gradient passes through unchanged
+  const bool ok = prm.rec_valid[b] != 0;
+  const double* rec = prm.rec + (size_t)b * nrmp_adj_doubles(T, prm.M);
+  // per-warp workspace: L (nL) | zU (nU) | qz (3T) | zD (T) | v (T)
+  double* w = smem_adj + (size_t)warp * (nL + nU + 5 * T);
+  double* L = w; double* zU = L + nL; double* qz = zU + nU; double* zD = qz + 3 * T; double* vv = zD + T;
+  auto hrow = [](int i) { return (i * (i + 3)) >> 1; };
+  if (!ok) {  // no usable factor (solver status != 0): no gradient through this solve
+    for (int i = lane; i < 3 * T1; i += 32) gs[i] = 0.0;
+    for (int i = lane; i < 2 * T; i += 32) gu[i] = 0.0;
+    for (int i = lane; i < T; i += 32) gd[i] = 0.0;
+    return;
+  }
+  for (int i = lane; i < nL; i += 32) L[i] = rec[i];
+  for (int t = lane; t < T; t += 32) vv[t] = hasD ? gd[t] * rec[oP + t] : 0.0;  // g_D / H_DD
+  __syncwarp();
+  // right-hand side of the U block:  g_U + F' g_S + sum_t F_t[xy]' n_t (g_D / H_DD)_t
+  double r0 = 0.0, r1 = 0.0;
+  for (int sl = 0; sl < 2; ++sl) {
+    const int j = lane + 32 * sl;
+    if (j < nU) {
+      double acc = gu[(j & 1) * T + (j >> 1)];
+      for (int t = j >> 1; t < T; ++t) {
+        const int o = t * (t + 1) + j;
+        const double fx = rec[oF + o], fy = rec[oF + FT + o], fth = rec[oF + 2 * FT + o];
+        acc += fx * (gs[t + 1] + rec[oP + T + t] * vv[t]) + fy * (gs[T1 + t + 1] + rec[oP + 2 * T + t] * vv[t]) + fth * gs[2 * T1 + t + 1];
+      }
+      if (sl == 0) r0 = acc; else r1 = acc;
+    }
+  }
+  const double invd0 = lane < nU ? rec[oI + lane] : 0.0, invd1 = lane + 32 < nU ? rec[oI + lane + 32] : 0.0;
+  for (int k = 0; k < nU; ++k) {  // L y = r
+    const double mine = k < 32 ? r0 * invd0 : r1 * invd1;
+    const double yk = __shfl_sync(0xffffffffu, mine, k & 31);
+    if (lane == (k & 31)) { if (k < 32) r0 = yk; else r1 = yk; }
+    if (lane > k && lane < nU) r0 -= L[hrow(lane) + k] * yk;
+    if (lane + 32 > k && lane + 32 < nU) r1 -= L[hrow(lane + 32) + k] * yk;
+  }
+  for (int k = nU - 1; k >= 0; --k) {  // L' z = y
+    const double mine = k < 32 ? r0 * invd0 : r1 * invd1;
+    const double xk = __shfl_sync(0xffffffffu, mine, k & 31);
+    if (lane == (k & 31)) { if (k < 32) r0 = xk; else r1 = xk; }
+    if (lane < k) r0 -= L[hrow(k) + lane] * xk;
+    if (lane + 32 < k) r1 -= L[hrow(k) + lane + 32] * xk;
+  }
+  if (lane < nU) zU[lane] = r0;
+  if (lane + 32 < nU) zU[lane + 32] = r1;
+  __syncwarp();
+  for (int t = lane; t < T; t += 32) {  // qz_r[t] = F_t[r] z_U,  z_D
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int i = 0; i < 2 * (t + 1); ++i) {
+      const int o = t * (t + 1) + i;
+      a0 += rec[oF + o] * zU[i]; a1 += rec[oF + FT + o] * zU[i]; a2 += rec[oF + 2 * FT + o] * zU[i];
+    }
+    qz[t] = a0; qz[T + t] = a1; qz[2 * T + t] = a2;
+    zD[t] = hasD ? (gd[t] + rec[oP + T + t] * a0 + rec[oP + 2 * T + t] * a1) * rec[oP + t] : 0.0;
+  }
+  __syncwarp();
+  // parameter gradients
+  const float* rs = prm.ref_s + (size_t)b * 3 * T1;
+  const float* rus = prm.ref_us + (size_t)b * T;
+  const int rows_s = prm.kin == 2 ? 2 : 3;
+  double dq[3] = {0, 0, 0}, dpu = 0, deta = 0, ddmax = 0, ddmin = 0;
+  for (int t = lane; t < T; t += 32) {
+    for (int r = 0; r < rows_s; ++r) dq[r] += -4.0 * (double)prm.q[r] * qz[r * T + t] * (rec[oS + r * T + t] - (double)rs[r * T1 + t + 1]);
+    dpu += -4.0 * (double)prm.p_u * zU[2 * t] * (rec[oU0 + t] - (double)rus[t]);
+    deta += zD[t];
+    ddmax += zD[t] * rec[oP + 3 * T + t];
+    ddmin += zD[t] * rec[oP + 4 * T + t];
+  }
+  for (int r = 0; r < 3; ++r) dq[r] = warp_sum(dq[r]);
+  dpu = warp_sum(dpu); deta = warp_sum(deta); ddmax = warp_sum(ddmax); ddmin = warp_sum(ddmin);
+  if (lane == 0) {
+    double* g = prm.grad_theta + (size_t)b * 7;
+    g[0] += dq[0]; g[1] += dq[1]; g[2] += dq[2]; g[3] += dpu; g[4] += deta; g[5] += ddmax;
+    g[6] += prm.d_min > 0.f ? ddmin : 0.0;  // the program uses max(d_min, 0) (nonneg Variable, nrmp.py:264-266)
+  }
+  __syncwarp();
+  // what flows on into the previous iteration: dL/dpara_s[r, t+1] = bk F_t[r] z_U; nothing through U, D or the initial column
+  for (int i = lane; i < 3 * T1; i += 32) {
+    const int r = i / T1, c = i - r * T1;
+    gs[i] = c == 0 ? 0.0 : prm.bk * qz[r * T + c - 1];
+  }
+  for (int i = lane; i < 2 * T; i += 32) gu[i] = 0.0;
+  for (int i = lane; i < T; i += 32) gd[i] = 0.0;
 }
 
 // Kernel: persistent warps.  Every warp owns one workspace in shared memory and pulls environments from a global counter

@@ -86,6 +86,10 @@ struct nb_pan {
   float *prev_s = nullptr, *prev_u = nullptr, *prev_mu = nullptr, *prev_lam = nullptr;
   int32_t *prev_count = nullptr, *prev_valid = nullptr, *active = nullptr, *iters = nullptr, *status = nullptr, *ipm_it = nullptr;
   float* min_dist = nullptr;
+  // differentiable mode (NB_OPT_DIFFERENTIABLE): adjoint records of every (iteration, env) solve + gradient workspaces
+  int differentiable = 0, adj_iters = 0;
+  double *adj_rec = nullptr, *adj_gs = nullptr, *adj_gu = nullptr, *adj_gd = nullptr, *adj_gtheta = nullptr;
+  int32_t* adj_valid = nullptr;
   int* work_counters = nullptr;     // dynamic env -> warp assignment of the NRMP kernel, one counter per internal stream
   int nrmp_dynamic = 1;             // NB_NRMP_STATIC=1 (developer switch, read at create) turns the persistent-warp schedule off
   float* warm = nullptr;            // NRMP warm-start records, nrmp_warm_floats(T, M) per environment
@@ -336,7 +340,7 @@ int nb_pan_destroy(nb_pan_t* p) {
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   void* bufs[] = {p->d_tc_image, p->d_image, p->d_weights, p->sel_mu, p->sel_lam, p->sel_pts, p->sel_dist, p->sel_count, p->prev_s, p->prev_u, p->prev_mu,
                   p->prev_lam, p->prev_count, p->prev_valid, p->active, p->iters, p->status, p->ipm_it, p->min_dist, p->h_in, p->h_out, p->h_np, p->h_io,
-                  p->warm, p->warm_valid, p->work_counters};
+                  p->warm, p->warm_valid, p->work_counters, p->adj_rec, p->adj_gs, p->adj_gu, p->adj_gd, p->adj_gtheta, p->adj_valid};
   for (void* b : bufs)
     if (b) cudaFree(b);
   delete p;
@@ -372,6 +376,11 @@ int nb_pan_set_option(nb_pan_t* p, int32_t option, int32_t value) {
     }
     if (value > 1 && !p->ev_fork) NB_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     p->overlap = value;
+    return NB_OK;
+  }
+  if (option == NB_OPT_DIFFERENTIABLE) {
+    if (value < 0 || value > 1) return fail(NB_ERR_INVALID, "NB_OPT_DIFFERENTIABLE takes 0 or 1");
+    p->differentiable = value;
     return NB_OK;
   }
   if (option == NB_OPT_NRMP_WARM) {
@@ -436,6 +445,21 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
   const nb_pan_config& c = p->cfg;
   const int T = c.receding, T1 = T + 1;
   const bool with_dune = c.nrmp_max_num > 0 && points != nullptr && N > 0;  // pan.py:130
+  if (p->differentiable && (p->adj_rec == nullptr || p->adj_iters < c.iter_num)) {  // (re)allocate the adjoint records for K iterations
+    void* old[] = {p->adj_rec, p->adj_valid, p->adj_gs, p->adj_gu, p->adj_gd, p->adj_gtheta};
+    for (void* o : old)
+      if (o) cudaFree(o);
+    p->adj_rec = nullptr; p->adj_valid = nullptr; p->adj_gs = p->adj_gu = p->adj_gd = p->adj_gtheta = nullptr;
+    const size_t Bm = c.max_envs, Ks = c.iter_num > 0 ? c.iter_num : 1;
+    NB_CUDA(dalloc(&p->adj_rec, Ks * Bm * nb::nrmp_adj_doubles(T, c.nrmp_max_num)));
+    NB_CUDA(dalloc(&p->adj_valid, Ks * Bm));
+    NB_CUDA(dalloc(&p->adj_gs, Bm * 3 * T1));
+    NB_CUDA(dalloc(&p->adj_gu, Bm * 2 * T));
+    NB_CUDA(dalloc(&p->adj_gd, Bm * T));
+    NB_CUDA(dalloc(&p->adj_gtheta, Bm * 7));
+    p->adj_iters = (int)Ks;
+  }
+  if (p->differentiable) NB_CUDA(cudaMemsetAsync(p->adj_valid, 0, (size_t)p->adj_iters * c.max_envs * sizeof(int32_t), st));
   const int tb = 128, gb = (B + tb - 1) / tb;
   init_run_kernel<<<gb, tb, 0, st>>>(B, p->active, p->iters, p->status, p->min_dist, p->sel_count, p->warm_valid);
   ++g_launches;
@@ -471,6 +495,10 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
       n.prev_s = p->prev_s + (size_t)lo * 3 * T1s; n.prev_u = p->prev_u + (size_t)lo * 2 * T;
       n.prev_mu = p->prev_mu + (size_t)lo * T1s * Ms * Es; n.prev_lam = p->prev_lam + (size_t)lo * T1s * Ms * 2;
       n.prev_count = p->prev_count + lo; n.prev_valid = p->prev_valid + lo;
+      if (p->differentiable && p->adj_rec && k < p->adj_iters) {
+        n.adj_save = p->adj_rec + ((size_t)k * c.max_envs + lo) * nb::nrmp_adj_doubles(T, c.nrmp_max_num);
+        n.adj_valid = p->adj_valid + (size_t)k * c.max_envs + lo;
+      }
       if (p->nrmp_warm) {
         n.warm = p->warm + (size_t)lo * nb::nrmp_warm_floats(T, c.nrmp_max_num);
         n.warm_valid = p->warm_valid + lo;
@@ -496,6 +524,57 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
     }
   }
   finish_run_kernel<<<gb, tb, 0, st>>>(B, p->iters, p->status, p->min_dist, out_iters, out_status, out_min_distance);
+  ++g_launches;
+  NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+
+namespace {
+__global__ void adj_load_kernel(int n_s, int n_u, int n_d, int n_t, const float* gs, const float* gu, const float* gd, double* ds, double* du, double* dd,
+                                double* dtheta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_s) ds[i] = gs ? (double)gs[i] : 0.0;
+  if (i < n_u) du[i] = gu ? (double)gu[i] : 0.0;
+  if (i < n_d) dd[i] = gd ? (double)gd[i] : 0.0;
+  if (i < n_t) dtheta[i] = 0.0;
+}
+__global__ void adj_store_kernel(int n, const double* dtheta, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)dtheta[i];
+}
+}  // namespace
+
+int nb_pan_backward(nb_pan_t* p, int32_t B, const float* ref_s, const float* ref_us, const float* grad_s, const float* grad_u, const float* grad_d,
+                    float* grad_theta, void* stream) {
+  if (int rc = check_forward_args(p, B, 0)) return rc;
+  if (!p->differentiable || !p->adj_rec) return fail(NB_ERR_INVALID, "nb_pan_backward needs a forward in differentiable mode (NB_OPT_DIFFERENTIABLE = 1) first");
+  if (!ref_s || !ref_us || !grad_theta) return fail(NB_ERR_INVALID, "null tensor argument");
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const nb_pan_config& c = p->cfg;
+  const int T = c.receding, T1 = T + 1, nU = 2 * T;
+  const int n_s = B * 3 * T1, n_u = B * 2 * T, n_d = B * T, n_t = B * 7;
+  const int tb = 256, gb = (n_s + tb - 1) / tb;
+  adj_load_kernel<<<gb, tb, 0, st>>>(n_s, n_u, n_d, n_t, grad_s, grad_u, grad_d, p->adj_gs, p->adj_gu, p->adj_gd, p->adj_gtheta);
+  ++g_launches;
+  nb::NrmpAdjParams a{};
+  a.iters = p->iters; a.ref_s = ref_s; a.ref_us = ref_us;
+  a.g_s = p->adj_gs; a.g_u = p->adj_gu; a.g_d = p->adj_gd; a.grad_theta = p->adj_gtheta;
+  a.B = B; a.T = T; a.M = c.nrmp_max_num; a.kin = c.kinematics;
+  for (int i = 0; i < 3; ++i) a.q[i] = c.q_s[i];
+  a.p_u = c.p_u; a.d_min = c.d_min; a.bk = c.bk;
+  const int wpc = 4;
+  const size_t smem = (size_t)wpc * (((size_t)nU * (nU + 3)) / 2 + nU + 5 * T) * sizeof(double);
+  if (smem > 48 * 1024) NB_CUDA(cudaFuncSetAttribute(nb::nrmp_adjoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int K = c.iter_num < p->adj_iters ? c.iter_num : p->adj_iters;
+  for (int k = K - 1; k >= 0; --k) {  // reverse over the PAN iterations: the gradient w.r.t. para_s chains into the previous solve
+    a.k = k;
+    a.rec = p->adj_rec + (size_t)k * c.max_envs * nb::nrmp_adj_doubles(T, c.nrmp_max_num);
+    a.rec_valid = p->adj_valid + (size_t)k * c.max_envs;
+    nb::nrmp_adjoint_kernel<<<(B + wpc - 1) / wpc, wpc * 32, smem, st>>>(a);
+    ++g_launches;
+  }
+  adj_store_kernel<<<(n_t + tb - 1) / tb, tb, 0, st>>>(n_t, p->adj_gtheta, grad_theta);
   ++g_launches;
   NB_CUDA(cudaGetLastError());
   return NB_OK;

@@ -63,7 +63,8 @@ class PlannerBatch:
         if ranges is not None:
             points, point_velocities, num_points = scan_to_points(states, ranges, scan, scan_offset, angle_range, down_sample,
                                                                   max_points=self.pan.dune_max_num, velocity=scan_velocity, device=self.device)
-        opt_s, opt_u, opt_d = self.pan(nom_s, nom_u, ref_s, ref_us, points, point_velocities, num_points)
+        with torch.no_grad():  # batched control is inference; tune parameters through neupan / PAN (differentiable mode) instead
+            opt_s, opt_u, opt_d = self.pan(nom_s, nom_u, ref_s, ref_us, points, point_velocities, num_points)
         arrive = arrived.bool()
         md = self.pan.min_distance
         md = md if torch.is_tensor(md) else torch.full((self.B,), float(md), device=self.device)

@@ -129,3 +129,67 @@ def backward(p: NrmpProblem, ref_s, ref_us, gS, gU, gD, tol=1e-7):
         db = (mp["bb"] - mm["bb"])[act] / (2 * h)
         out[i] = z @ np.concatenate([-dg, db])
     return out
+
+
+def backward_full(p: NrmpProblem, ref_s, ref_us, gS, gU, gD, tol=1e-7):
+    """``backward`` plus the gradient that flows on into the previous PAN iteration: returns (dL/dtheta (7), dL/dpara_s (3,T+1)).
+    ``para_s`` is the NRMP parameter the reference feeds with ``nom_s`` (nrmp.py:156, robot.py:243): the output S of the previous
+    solve, a tensor that carries its autograd history.  It enters the program through the proximal term only
+    (0.5 bk |S - para_s|^2, nrmp.py:350); its first column also pins S[:, 0], but that column is the same constant in every
+    iteration, so its gradient is not needed (returned as zero)."""
+    S, U, D, _ = ipm.solve_ipm(p)
+    x = _x_of(p, U, D)
+    m = ipm.assemble(p)
+    act, hinge = active_sets(p, x, tol)
+    A = m["Ab"][act]
+    H = m["P"] + (m["rho"] * m["J"][hinge].T @ m["J"][hinge] if p.M > 0 else 0.0)
+    n, na, nU, T = m["n"], A.shape[0], m["nU"], p.T
+    K = np.zeros((n + na, n + na))
+    K[:n, :n], K[:n, n:], K[n:, :n] = H, A.T, A
+    gx = np.zeros(n)
+    gx[:nU] = np.asarray(gU, np.float64).T.reshape(-1)
+    for t in range(T):
+        gx[:nU] += m["F"][t].T @ np.asarray(gS, np.float64)[:, t + 1]
+    if p.M > 0:
+        gx[nU:] = np.asarray(gD, np.float64).reshape(-1)
+    z = np.linalg.lstsq(K.T, np.concatenate([gx, np.zeros(na)]), rcond=None)[0]
+    g_theta = backward(p, ref_s, ref_us, gS, gU, gD, tol)
+    g_para = np.zeros((3, T + 1))
+    for t in range(T):
+        g_para[:, t + 1] = p.bk * (m["F"][t] @ z[:nU])  # dF/dpara_s[r,t+1] = -bk F_t[r]'  ->  dL/dpara_s = +bk F_t[r] z
+    return g_theta, g_para
+
+
+def backward_chain(problems, ref_s, ref_us, gS, gU, gD, tol=1e-7):
+    """Reference semantics of ``loss.backward()`` through PAN.forward (pan.py:127-147): the K solves are chained through ``nom_s``
+    only -- A, B, C (robot.py:272-316: ``torch.Tensor([...])`` of detached numbers), fa, fb (dune.py:78-95 under ``no_grad``, R built
+    by ``torch.tensor``) and nom_u carry no gradient.  ``problems`` = the K NrmpProblems in execution order; (gS, gU, gD) = upstream
+    gradient of the LAST solve's outputs.  Returns dL/dtheta (7)."""
+    total = np.zeros(7)
+    gS = np.asarray(gS, np.float64).copy()
+    gU = np.asarray(gU, np.float64).copy()
+    gD = np.asarray(gD, np.float64).copy()
+    for p in reversed(problems):
+        g_theta, g_para = backward_full(p, ref_s, ref_us, gS, gU, gD, tol)
+        total += g_theta
+        gS, gU, gD = g_para, np.zeros_like(gU), np.zeros_like(gD)
+    return total
+
+
+def chain_loss(problems, ref_s, ref_us, theta, wS, wU, wD):
+    """L(theta) = <wS, S_K> + <wU, U_K> + <wD, D_K> of the K-solve chain with FROZEN coefficients: solve k uses problems[k]'s
+    A, B, C, fa, fb and (theta, para_s = S_{k-1}(theta)) -- the function whose gradient backward_chain states.  For finite
+    differences in the tests."""
+    S_prev = None
+    for k, p in enumerate(problems):
+        q = with_theta(p, ref_s, ref_us, theta)
+        if S_prev is not None:
+            ns = q.nom_s.copy()
+            ns[:, 1:] = S_prev[:, 1:]
+            q = dataclasses.replace(q, nom_s=ns)
+        S, U, D, _ = ipm.solve_ipm(q)
+        S_prev = S
+    val = float(np.sum(wS * S) + np.sum(wU * U))
+    if problems[-1].M > 0:
+        val += float(np.sum(wD * D.reshape(-1)))
+    return val

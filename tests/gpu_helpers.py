@@ -19,7 +19,8 @@ def to_cuda(inp):
 
 def run_pan(pan, inp, cuda=True):
     t = to_cuda(inp) if cuda else {k: (None if v is None else torch.from_numpy(v)) for k, v in inp.items()}
-    S, U, D = pan(t["nom_s"], t["nom_u"], t["ref_s"], t["ref_us"], t["points"], t["velocities"])
+    with torch.no_grad():  # inference: with autograd recording, PAN runs in differentiable mode (tests/test_gpu_grad.py)
+        S, U, D = pan(t["nom_s"], t["nom_u"], t["ref_s"], t["ref_us"], t["points"], t["velocities"])
     return S.cpu().numpy(), U.cpu().numpy(), D.cpu().numpy()[:, 0], pan.min_distance.cpu().numpy()
 
 

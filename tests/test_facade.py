@@ -133,7 +133,8 @@ def test_facade_step_matches_oracle(tmp_path):
     cfg = CONFIGS["C1"]
     o = oracle_factory(cfg, K=1, N=100)()
     S, U, D = o.forward(ns.astype(np.float32), nu.astype(np.float32), rs.astype(np.float32), rus.astype(np.float32), pts.astype(np.float32), None)
-    assert rel_err(info["vel_tensor"].numpy(), U) < 1e-4 and rel_err(info["state_tensor"].numpy(), S) < 1e-4
+    assert rel_err(info["vel_tensor"].detach().numpy(), U) < 1e-4 and rel_err(info["state_tensor"].detach().numpy(), S) < 1e-4
+    assert info["state_tensor"].requires_grad  # like the reference: the planner's output carries the graph to NRMP.adjust_parameters (LON)
     assert np.allclose(action[:, 0], U[:, 0], atol=1e-4)
 
 
