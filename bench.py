@@ -709,6 +709,59 @@ def run_control(args):
                                    api="neupan_b200.PlannerBatch.forward on pinned host states + scans -> actions on the host"))))
 
 
+# --------------------------------------------------------------------------------------------
+# --workload train: DUNE training epochs (SURVEY 8f "next" row 4)
+def run_train(args):
+    """metric: training epochs/s of the reference's default data set (data_size 100,000 -> 80,000 training points, batch 256 = 313
+    sequential Adam steps per epoch).  value: nb_dune_train_epoch (one persistent CTA, parameters in shared memory);  cpu_baseline /
+    --impl reference: the same loop in eager torch on the host cores (the restatement of dune_train.py:281-362; torch picks its threads)."""
+    import torch
+
+    from helpers import CONFIGS
+    from neupan_b200 import _lib
+    from neupan_b200.blocks.dune_train import DUNETrain
+    from neupan_b200.blocks.obs_point_net import ObsPointNet
+
+    rb = CONFIGS["C4"].make_robot()
+    G, h = np.asarray(rb.G, np.float32), np.asarray(rb.h, np.float32).reshape(-1)
+    n_total, batch = 100000, 256
+    torch.manual_seed(0); np.random.seed(0)
+    reference = args.impl == "reference"
+    tr = DUNETrain(ObsPointNet(2, G.shape[0]), G, h, "/tmp/neupan_b200_bench_train", backend="torch" if reference else "native")
+    tr.optimizer.param_groups[0]["lr"] = 5e-5
+    t0 = time.perf_counter()
+    pts, mu, dist = tr.generate_data_set(n_total, [-25, -25, 25, 25])
+    if not reference:
+        torch.cuda.synchronize()
+    label_s = time.perf_counter() - t0
+    n = int(n_total * 0.8)
+    data = (pts[:n], mu[:n], dist[:n])
+    steps = max(1, min(args.steps, 2)) if reference else args.steps
+    for _ in range(1 if reference else args.warmup):
+        tr.train_one_epoch(data, batch, False)
+    l0 = _lib.load().nb_launch_count() if not reference else 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        losses = tr.train_one_epoch(data, batch, False)  # synchronises (the losses come back to the host)
+    wall = time.perf_counter() - t0
+    ms = 1e3 * wall / steps
+    line = dict(metric="DUNE training epochs/sec (80,000 points, batch 256, Adam)", value=steps / wall, unit="epochs/s", n_gpus=1, steps=steps,
+                warmup=1 if reference else args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=f"train: {n} points x 313 Adam steps per epoch, E={G.shape[0]}, labels in closed form ({label_s:.3f} s for {n_total} points)"),
+                loss_after=float(sum(losses)), optimizer_steps_per_s=steps * ((n + batch - 1) // batch) / wall)
+    if reference:
+        line.update(impl="reference", gpu_launches=0, e2e=dict(value=steps / wall, unit="epochs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    cpu_baseline=dict(value=steps / wall, unit="epochs/s", cores=torch.get_num_threads(), kind="port",
+                                      sample=f"{steps} epoch(s); neupan_b200.blocks.dune_train backend='torch' on the CPU = the reference's loop (dune_train.py:281-362) with closed-form labels"))
+    else:
+        line.update(gpu_launches=int((_lib.load().nb_launch_count() - l0) // steps),
+                    e2e=dict(value=steps / wall, unit="epochs/s", h2d_bytes_per_step=4 * ((n + batch - 1) // batch), d2h_bytes_per_step=32, ms_per_step=ms,
+                             api="DUNETrain.train_one_epoch(backend='native'): data resident on the device, per epoch the batch rotations go in and the four loss means come out"),
+                    roofline=dict(bound="latency", achieved=None, peak=None, unit=None, frac=None, traffic=None, kernel="dune_train_epoch_kernel (1 persistent CTA)",
+                                  note="313 strictly sequential optimiser steps of 20 MFLOP each: neither HBM nor a math pipe is the limit; see csrc/dune_train_kernel.cuh"))
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -725,7 +778,9 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, help="env sub-batches pipelined on internal streams (NB_OPT_OVERLAP)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.workload == "control" and args.impl == "ours":
+    if args.workload == "train":
+        run_train(args)
+    elif args.workload == "control" and args.impl == "ours":
         run_control(args)
     elif args.workload == "ipath" and args.impl == "ours":
         run_ipath(args)

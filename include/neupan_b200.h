@@ -242,6 +242,32 @@ int nb_ipath_reset_async(nb_ipath_t* ip, void* stream);   /* ordered with the st
 int nb_ipath_read_state(nb_ipath_t* ip, int32_t B, int32_t* curve_index, int32_t* point_index, int32_t* arrive_flag,
                         double* points_host, void* stream);
 
+/* ---- DUNE training on the device (SURVEY 8f "next" row 4) ------------------------------------------------------------ */
+
+/* DUNETrain.generate_data_set / prob_solve (neupan/blocks/dune_train.py:100-140): labels of n sampled points -- the solution of the
+ * cone program (10) max mu'(G p - h) s.t. |G' mu| <= 1, mu >= 0, in closed form (the reference calls cvxpy/ECOS once per point).
+ * HOST: G (E x 2), h (E).  DEVICE: points (n,2) float64 in, points_f32 (n,2), mu (n,E), dist (n) float32 out. */
+int nb_dune_labels(int32_t edge_dim, const float* G, const float* h, int64_t n, const double* points,
+                   float* points_f32, float* mu, float* dist, void* stream);
+
+typedef struct nb_dune_train nb_dune_train_t; /* owns the parameters being trained and Adam's moments */
+
+/* DUNETrain.__init__ (dune_train.py:61-80): weights (HOST, packed like nb_pan_create's) are the initial parameters; the optimiser is
+ * Adam(lr, betas (0.9, 0.999), eps 1e-8, weight_decay 1e-4) as at :72. */
+int nb_dune_train_create(int32_t edge_dim, const float* G, const float* h, const float* weights, int64_t n_weights,
+                         int32_t device, nb_dune_train_t** out);
+int nb_dune_train_destroy(nb_dune_train_t* t);
+
+/* DUNETrain.train_one_epoch (dune_train.py:281-333): one pass over n labelled points (DEVICE: pts (n,2), mu (n,E), dist (n)) in
+ * batches of batch_size <= 256 taken in order (DataLoader without shuffling), loss MSE(mu) + MSE(distance) + MSE(fa) + MSE(fb) with
+ * the rotation angle thetas[b] (HOST, one per batch; the reference draws np.random.uniform(0, 2 pi) per batch, :351) and, unless
+ * `validate`, one Adam step per batch.  losses (HOST, 4 doubles) = the four terms averaged over the batches.  Synchronises `stream`. */
+int nb_dune_train_epoch(nb_dune_train_t* t, const float* pts, const float* mu, const float* dist, int64_t n, int32_t batch_size,
+                        const float* thetas, float lr, int32_t validate, double* losses, void* stream);
+
+/* The current parameters (HOST, packed): torch.save(model.state_dict()) at :247-252 after unpacking. */
+int nb_dune_train_get_weights(nb_dune_train_t* t, float* weights);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t nb_launch_count(void);
 const char* nb_last_error(void);

@@ -80,6 +80,11 @@ SYMBOLS = {
     "nb_ipath_reset": (C.c_int, [C.c_void_p]),
     "nb_ipath_reset_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nb_ipath_read_state": (C.c_int, [C.c_void_p, C.c_int32, _FP, _FP, _FP, _FP, C.c_void_p]),
+    "nb_dune_labels": (C.c_int, [C.c_int32, _FP, _FP, C.c_int64, _FP, _FP, _FP, _FP, C.c_void_p]),
+    "nb_dune_train_create": (C.c_int, [C.c_int32, _FP, _FP, _FP, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "nb_dune_train_destroy": (C.c_int, [C.c_void_p]),
+    "nb_dune_train_epoch": (C.c_int, [C.c_void_p, _FP, _FP, _FP, C.c_int64, C.c_int32, _FP, C.c_float, C.c_int32, _FP, C.c_void_p]),
+    "nb_dune_train_get_weights": (C.c_int, [C.c_void_p, _FP]),
     "nb_launch_count": (C.c_int64, []),
     "nb_last_error": (C.c_char_p, []),
     "nb_version": (C.c_int, []),
@@ -117,6 +122,22 @@ def check(rc: int):
     if rc == NB_ERR_CAPACITY:
         raise ValueError("capacity exceeded: " + msg)
     raise NeupanB200Error(msg)
+
+
+def unpack_weights(flat: np.ndarray, reference_state_dict) -> dict:
+    """Inverse of pack_weights: a flat float32 vector -> {key: tensor} with the shapes of `reference_state_dict`."""
+    import torch
+
+    out, off = {}, 0
+    for idx in (0, 1, 3, 5, 6, 8, 10, 11, 13):
+        for kind in ("weight", "bias"):
+            key = f"MLP.{idx}.{kind}"
+            shape = tuple(reference_state_dict[key].shape)
+            n = int(np.prod(shape))
+            out[key] = torch.from_numpy(np.array(flat[off:off + n], dtype=np.float32).reshape(shape))
+            off += n
+    assert off == flat.size
+    return out
 
 
 def pack_weights(state_dict) -> np.ndarray:

@@ -14,6 +14,7 @@
 #include "nrmp_kernel.cuh"
 #include "scan_kernel.cuh"
 #include "ipath_kernel.cuh"
+#include "dune_train_kernel.cuh"
 
 #include <vector>
 
@@ -65,6 +66,16 @@ struct nb_ipath {
   int32_t* d_curve_index = nullptr;
   int32_t* d_point_index = nullptr;
   int32_t* d_arrive_flag = nullptr;
+};
+
+struct nb_dune_train {
+  int E = 0, device = 0, n_weights = 0;
+  float G[nb::kMaxEdges][2];
+  float h[nb::kMaxEdges];
+  float *d_weights = nullptr, *d_m = nullptr, *d_v = nullptr, *d_thetas = nullptr;
+  double* d_losses = nullptr;
+  size_t thetas_cap = 0;
+  long long steps = 0;  // optimiser steps taken so far (Adam bias correction)
 };
 
 struct nb_pan {
@@ -690,6 +701,100 @@ int nb_scan_to_points(int32_t B, int32_t R, const float* ranges, const float* ve
   }
   ++g_launches;
   NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+
+// ---- DUNE training -------------------------------------------------------------------------------
+int nb_dune_labels(int32_t E, const float* G, const float* h, int64_t n, const double* points, float* points_f32, float* mu, float* dist, void* stream) {
+  if (E < 3 || E > nb::kMaxEdges || !G || !h) return fail(NB_ERR_INVALID, "nb_dune_labels: edge_dim must be in 3..%d and G, h given", nb::kMaxEdges);
+  if (n < 0 || (n > 0 && (!points || !points_f32 || !mu || !dist))) return fail(NB_ERR_INVALID, "nb_dune_labels: null argument");
+  if (n == 0) return NB_OK;
+  nb::DuneLabelParams prm;
+  prm.n = (int)n; prm.E = E;
+  for (int e = 0; e < E; ++e) { prm.G[e][0] = G[2 * e]; prm.G[e][1] = G[2 * e + 1]; prm.h[e] = h[e]; }
+  prm.points = points; prm.points_f32 = points_f32; prm.mu = mu; prm.dist = dist;
+  nb::dune_label_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(prm);
+  ++g_launches;
+  NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+
+int nb_dune_train_create(int32_t E, const float* G, const float* h, const float* weights, int64_t n_weights, int32_t device, nb_dune_train_t** out) {
+  if (!out || !G || !h || !weights) return fail(NB_ERR_INVALID, "nb_dune_train_create: null argument");
+  *out = nullptr;
+  if (E < 3 || E > nb::kMaxEdges) return fail(NB_ERR_INVALID, "edge_dim must be in 3..%d", nb::kMaxEdges);
+  if (n_weights != nb::WeightLayout::count(E)) return fail(NB_ERR_INVALID, "expected %d weights for edge_dim %d", nb::WeightLayout::count(E), E);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
+    return fail(NB_ERR_NO_DEVICE, "no CUDA device available: neupan_b200 has no CPU fallback");
+  NB_CUDA(cudaSetDevice(device));
+  nb_dune_train* t = new (std::nothrow) nb_dune_train();
+  if (!t) return fail(NB_ERR_INVALID, "out of host memory");
+  t->E = E; t->device = device; t->n_weights = (int)n_weights;
+  for (int e = 0; e < E; ++e) { t->G[e][0] = G[2 * e]; t->G[e][1] = G[2 * e + 1]; t->h[e] = h[e]; }
+  cudaError_t e = dalloc(&t->d_weights, (size_t)n_weights);
+  if (e == cudaSuccess) e = dalloc(&t->d_m, (size_t)n_weights);
+  if (e == cudaSuccess) e = dalloc(&t->d_v, (size_t)n_weights);
+  if (e == cudaSuccess) e = dalloc(&t->d_losses, (size_t)4);
+  if (e == cudaSuccess) e = cudaMemcpy(t->d_weights, weights, (size_t)n_weights * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(t->d_m, 0, (size_t)n_weights * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(t->d_v, 0, (size_t)n_weights * sizeof(float));
+  if (e != cudaSuccess) {
+    nb_dune_train_destroy(t);
+    return fail(NB_ERR_CUDA, "nb_dune_train_create: %s", cudaGetErrorString(e));
+  }
+  *out = t;
+  return NB_OK;
+}
+
+int nb_dune_train_destroy(nb_dune_train_t* t) {
+  if (!t) return NB_OK;
+  cudaSetDevice(t->device);
+  void* bufs[] = {t->d_weights, t->d_m, t->d_v, t->d_thetas, t->d_losses};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  delete t;
+  return NB_OK;
+}
+
+int nb_dune_train_epoch(nb_dune_train_t* t, const float* pts, const float* mu, const float* dist, int64_t n, int32_t batch, const float* thetas,
+                        float lr, int32_t validate, double* losses, void* stream) {
+  if (!t || !pts || !mu || !dist || !thetas || !losses) return fail(NB_ERR_INVALID, "nb_dune_train_epoch: null argument");
+  if (n < 1 || batch < 1 || batch > nb::kTrainThreads) return fail(NB_ERR_INVALID, "nb_dune_train_epoch: n >= 1 and 1 <= batch_size <= %d required", nb::kTrainThreads);
+  NB_CUDA(cudaSetDevice(t->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nbatch = (size_t)((n + batch - 1) / batch);
+  if (nbatch > t->thetas_cap) {
+    if (t->d_thetas) cudaFree(t->d_thetas);
+    t->d_thetas = nullptr; t->thetas_cap = 0;
+    NB_CUDA(dalloc(&t->d_thetas, nbatch));
+    t->thetas_cap = nbatch;
+  }
+  NB_CUDA(cudaMemcpyAsync(t->d_thetas, thetas, nbatch * sizeof(float), cudaMemcpyHostToDevice, st));
+  nb::DuneTrainParams prm;
+  prm.pts = pts; prm.mu = mu; prm.dist = dist; prm.thetas = t->d_thetas;
+  prm.weights = t->d_weights; prm.adam_m = t->d_m; prm.adam_v = t->d_v; prm.losses = t->d_losses;
+  prm.n = (int)n; prm.batch = batch; prm.E = t->E; prm.validate = validate ? 1 : 0;
+  prm.step0 = t->steps;
+  prm.lr = lr; prm.beta1 = 0.9f; prm.beta2 = 0.999f; prm.eps = 1e-8f; prm.weight_decay = 1e-4f;  // Adam(lr, weight_decay=1e-4), dune_train.py:72
+  for (int e = 0; e < nb::kMaxEdges; ++e) { prm.G[e][0] = t->G[e][0]; prm.G[e][1] = t->G[e][1]; prm.h[e] = t->h[e]; }
+  const size_t smem = nb::dune_train_smem_bytes(t->E);
+  NB_CUDA(cudaFuncSetAttribute(nb::dune_train_epoch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nb::dune_train_epoch_kernel<<<1, nb::kTrainThreads, smem, st>>>(prm);
+  ++g_launches;
+  NB_CUDA(cudaGetLastError());
+  double sums[4];
+  NB_CUDA(cudaMemcpyAsync(sums, t->d_losses, sizeof(sums), cudaMemcpyDeviceToHost, st));
+  NB_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < 4; ++i) losses[i] = sums[i] / (double)nbatch;  // mean over the batches, like train_one_epoch (:322-327)
+  if (!validate) t->steps += (long long)nbatch;
+  return NB_OK;
+}
+
+int nb_dune_train_get_weights(nb_dune_train_t* t, float* weights) {
+  if (!t || !weights) return fail(NB_ERR_INVALID, "nb_dune_train_get_weights: null argument");
+  NB_CUDA(cudaSetDevice(t->device));
+  NB_CUDA(cudaMemcpy(weights, t->d_weights, (size_t)t->n_weights * sizeof(float), cudaMemcpyDeviceToHost));
   return NB_OK;
 }
 
