@@ -382,6 +382,7 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
   const bool warm = try_warm && attempt == 0;
   bool restart = false;
   stat &= ~3;
+  __syncwarp();  // a restart re-initialises shared state the abandoned attempt was still reading (ordered only by shuffles)
   NB_LL(i, nU) x[i] = warm ? (1.0 - kTheta) * (double)wrec[i] : 0.0;
   NB_LL(t, TD) Dv[t] = dfix ? dlo : (warm ? (1.0 - kTheta) * (double)wrec[nU + t] + kTheta * dmid : dmid);
   __syncwarp();

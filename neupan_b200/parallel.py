@@ -72,7 +72,8 @@ class ShardedPAN:
         if host:
             up = lambda t: None if t is None else t.to(pan.device, non_blocking=True)
             nom_s, nom_u, ref_s, ref_us, points, velocities, num_points = (up(t) for t in (nom_s, nom_u, ref_s, ref_us, points, velocities, num_points))
-        S, U, D = pan(nom_s, nom_u, ref_s, ref_us, points, velocities, num_points)
+        with torch.no_grad():  # sharded control is inference (the gather is not differentiable); tune parameters through PAN itself
+            S, U, D = pan(nom_s, nom_u, ref_s, ref_us, points, velocities, num_points)
         B = S.shape[0]
         md = pan.min_distance if torch.is_tensor(pan.min_distance) else torch.full((B,), float("inf"), device=S.device)
         if D is None:

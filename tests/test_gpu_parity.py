@@ -204,6 +204,23 @@ def test_c4_env_934_iteration_5():
     assert err < TOL
 
 
+@pytest.mark.parametrize("cname", ["C1", "C2", "C4", "C5"])
+def test_single_iteration_vs_reference_pan_golden(cname):
+    """Directly against the REFERENCE'S OWN PAN.forward (tests/golden/ref_pan.npz, made by make_golden_refpan.py: pan.py / dune.py /
+    nrmp.py / robot.py executing unmodified, cvxpy + cvxpylayers replaced by the numeric shim): one PAN iteration per environment."""
+    z = np.load(f"{GOLDEN}/ref_pan.npz")
+    cfg = CONFIGS[cname]
+    S0, N = z[f"{cname}_S"], int(z[f"{cname}_N"])
+    nenv = S0.shape[0]
+    inp = make_inputs(cfg, B=nenv, N=N, scene="obstacles")
+    pan = make_pan(cfg, K=1, N=N, max_envs=nenv)
+    S, U, D, md = run_pan(pan, inp)
+    err = [max(rel_err(S[b], S0[b]), rel_err(U[b], z[f"{cname}_U"][b]), rel_err(D[b], z[f"{cname}_D"][b][0]), abs(md[b] - z[f"{cname}_md"][b])) for b in range(nenv)]
+    record("vs_reference_pan_golden", config=cname, envs=nenv, max_err=float(max(err)))
+    bad = [b for b in range(nenv) if err[b] >= TOL and not _excused(cfg, inp, b, inp["nom_s"][b], inp["nom_u"][b])]
+    assert not bad, (bad, err)
+
+
 def test_host_and_device_entry_points_agree():
     cfg = CONFIGS["C2"]
     inp = make_inputs(cfg, B=5)
