@@ -1091,7 +1091,11 @@ __global__ void __launch_bounds__(128) nrmp_adjoint_kernel(const NrmpAdjParams p
 // a static env -> warp map leaves the fast warps of a wave idle (and a CTA slot is only re-used when BOTH its warps are done).
 // work_counter == nullptr: one environment per warp (b = blockIdx.x * warps + warp), the grid covers the batch.
 template <int HPL, bool SMALL, int TT, int MM>
-__global__ void __launch_bounds__(64, (TT == 10 && MM == 10) ? 7 : (HPL <= 4 ? 6 : 4)) nrmp_kernel(const NrmpParams prm, int warps_per_cta, int warp_doubles_rt) {
+#ifndef NB_NRMP_WPC
+#define NB_NRMP_WPC 3  // warps per CTA of the (10, 10) specialisation: 3 x 5 CTAs = 15 warps per SM (2 x 7 = 14: 29.29 vs 29.02 ms per step; 1 x 14: 29.64)
+#endif
+__global__ void __launch_bounds__((TT == 10 && MM == 10) ? 32 * NB_NRMP_WPC : 64, (TT == 10 && MM == 10) ? (NB_NRMP_WPC == 3 ? 5 : (NB_NRMP_WPC == 1 ? 14 : 7)) : (HPL <= 4 ? 6 : 4))
+    nrmp_kernel(const NrmpParams prm, int warps_per_cta, int warp_doubles_rt) {
   extern __shared__ __align__(16) double smem_d[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int T = TT > 0 ? TT : prm.T, M = TT > 0 ? MM : prm.M;

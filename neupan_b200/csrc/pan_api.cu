@@ -201,6 +201,7 @@ int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st, int counter_slot
   if (warps < 1) return fail(NB_ERR_CAPACITY, "T=%d, M=%d need %zu B of shared memory per environment", prm.T, prm.M, wd * 8);
   // small CTAs (<= 2 warps): many of them fit per SM and each warp retires independently
   if (warps > 2) warps = 2;
+  if (prm.T == 10 && prm.M == 10) warps = NB_NRMP_WPC;
   const size_t smem = (size_t)warps * wd * sizeof(double) + extra;
   int grid = (prm.B + warps - 1) / warps;
   auto go = [&](auto kern) -> int {

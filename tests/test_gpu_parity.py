@@ -221,6 +221,18 @@ def test_single_iteration_vs_reference_pan_golden(cname):
     assert not bad, (bad, err)
 
 
+def test_default_two_iterations_vs_reference_pan_golden():
+    """BASELINE config 1 with the reference's default iter_num = 2: the whole forward against the reference's own PAN.forward
+    (golden through the shim).  Two chained iterations: statistical like test_end_to_end_two_iterations_vs_live_oracle."""
+    z = np.load(f"{GOLDEN}/ref_pan.npz")
+    cfg = CONFIGS["C1"]
+    inp = make_inputs(cfg, B=6, N=100, scene="obstacles")
+    S, U, D, md = run_pan(make_pan(cfg, K=2, N=100, max_envs=6), inp)
+    err = np.array([max(rel_err(S[b], z["C1k2_S"][b]), rel_err(U[b], z["C1k2_U"][b]), rel_err(D[b], z["C1k2_D"][b][0]), abs(md[b] - z["C1k2_md"][b])) for b in range(6)])
+    record("vs_reference_pan_golden_k2", config="C1", envs=6, within_tol=int((err < TOL).sum()), max_err=float(err.max()))
+    assert (err < TOL).mean() >= 0.8 and np.median(err) < TOL
+
+
 def test_host_and_device_entry_points_agree():
     cfg = CONFIGS["C2"]
     inp = make_inputs(cfg, B=5)
