@@ -376,7 +376,13 @@ def run_ours(args):
         ach = flops / (dune_ms * 1e-3) / 1e12
         alg_bytes = 4.0 * B * ((2 * N) * (2 if cfg.dynamic else 1) + 3 * (T + 1)) + 4.0 * B * (T + 1) * cfg.M * 9
         # executed tensor work (3 passes of the fp16 hi/lo split): per 128-point tile 4 layers x 6 UMMA (128x32x16) + head 6 UMMA (128x16x16)
-        if args.dune_kernel == 3:
+        if args.dune_kernel == 4:
+            tiles = B * (T + 1) * ((N + 127) // 128)
+            exec_flops = tiles * 5 * 3 * 2.0 * 128 * 32 * 16  # screening pass: bias product + one fp16 pass (2 UMMA 128x32x16) per layer; + ~7 % for the refined candidates
+            kname = ("dune_screen_kernel + dune_refine_kernel + dune_tcp_kernel (tcgen05.mma kind::f16: single-pass fp16 interval screening of all points, "
+                     "fp16 hi/lo 3-pass exact network for the <= 32 candidates per item, full kernel for the items the screen cannot narrow down; "
+                     "bit-identical selection to the full kernel; SASS UTCHMMA / LDTM / STTM / MUFU.TANH)")
+        elif args.dune_kernel == 3:
             tiles = B * (T + 1) * ((N + 127) // 128)
             exec_flops = tiles * 5 * 7 * 2.0 * 128 * 32 * 16
             kname = "dune_tc8_kernel (tcgen05.mma kind::f16, A from TMEM, fp16 hi/lo split, 3 passes + bias product; two threads per point = 8 warps per 128-point tile, two tiles in flight per CTA; SASS UTCHMMA / LDTM / STTM)"
@@ -772,7 +778,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="override B per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sides", action="store_true", help="skip the side measurements (other BASELINE configs / strong split / iter_threshold=0.1)")
-    ap.add_argument("--dune-kernel", type=int, default=2, help="NB_OPT_DUNE_KERNEL: 0 fp32 ffma, 1 mma.sync, 2 tcgen05 (thread per point), 3 tcgen05 (two threads per point)")
+    ap.add_argument("--dune-kernel", type=int, default=4, help="NB_OPT_DUNE_KERNEL: 0 fp32 ffma, 1 mma.sync, 2 tcgen05 (every point exactly), 3 tcgen05 (two threads per point), 4 tcgen05 with screening (default)")
     ap.add_argument("--iter-threshold", type=float, default=0.0, help="PAN stop criterion (pan.py:243); 0 forces exactly K iterations (the headline), the reference default is 0.1")
     ap.add_argument("--nrmp-warm", type=int, default=0, help="NB_OPT_NRMP_WARM: 1 = NRMP solves of PAN iterations k > 0 start from iteration k-1's solution")
     ap.add_argument("--overlap", type=int, default=1, help="env sub-batches pipelined on internal streams (NB_OPT_OVERLAP)")

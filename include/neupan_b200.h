@@ -121,7 +121,10 @@ int nb_pan_set_iteration(nb_pan_t* pan, int32_t iter_num, float iter_threshold);
  * iteration k-1 of the same environment (fewer interior point iterations on average, same optimum to the solver tolerance;
  * a warm start that is not converging by its 12th iteration is abandoned for a cold one); 0 (default) = every solve starts
  * cold.  The first solve of every call is always cold, so results never depend on earlier calls.
- * NB_OPT_DUNE_KERNEL also takes 3 = tcgen05 with two threads per point (8 warps per 128-point tile; measured slower, kept for A/B).
+ * NB_OPT_DUNE_KERNEL also takes 3 = tcgen05 with two threads per point (8 warps per 128-point tile; measured slower, kept for A/B)
+ * and 4 = tcgen05 with screening: a single-pass fp16 interval pass over all points, the exact network only for the <= 32 points
+ * per (environment, step) that can be among the M closest, the exact kernel for the items the screen cannot narrow down -- the same
+ * selection and values as 2, bit for bit (csrc/dune_screen_kernel.cuh).
  * NB_OPT_DIFFERENTIABLE: 1 = every NRMP solve of nb_pan_forward also stores what nb_pan_backward needs (one extra factorisation
  * at the optimum + ~5 KB per environment and iteration); 0 (default) = inference only. */
 enum { NB_OPT_DUNE_KERNEL = 1, NB_OPT_OVERLAP = 2, NB_OPT_NRMP_WARM = 3, NB_OPT_DIFFERENTIABLE = 4 };
@@ -150,6 +153,12 @@ int nb_pan_reset_state_async(nb_pan_t* pan, void* stream);   /* ordered with the
  * sel_points[:,0] is NRMP.points / PAN.nrmp_points (nrmp.py:135-138, pan.py:262-268). */
 int nb_pan_read_selection(nb_pan_t* pan, int32_t B, float* sel_mu, float* sel_lam, float* sel_points,
                           float* sel_distance, int32_t* sel_count, void* stream);
+
+/* Screening statistics accumulated since the last reset (HOST outputs; synchronises the device): max_error_ratio[0] = the largest
+ * |screened - exact distance| / sum_e |G_e p0 - h_e| over all refined candidates, [1] = the handle's bound c_mu it must stay below
+ * (4 x the error measured at calibration, when NB_OPT_DUNE_KERNEL = 4 is first selected), [2] = that calibration measurement;
+ * counts[0] = items sent to the exact kernel, counts[1] = candidates refined, counts[2] = items screened. */
+int nb_pan_read_screen_stats(nb_pan_t* pan, float* max_error_ratio, int32_t* counts, int32_t reset);
 
 /* Diagnostics of the last executed NRMP solve: interior point iterations per env (B) int32. */
 int nb_pan_read_diagnostics(nb_pan_t* pan, int32_t B, int32_t* ipm_iterations, void* stream);

@@ -7,6 +7,7 @@ namespace nb {
 
 constexpr int kHidden = 32;   // ObsPointNet hidden width (obs_point_net.py:29)
 constexpr int kMaxEdges = 8;  // largest supported E = G.shape[0]
+constexpr int kCandMax = 32;  // candidates per (environment, step) item kept by the DUNE screening pass (dune_screen_kernel.cuh)
 
 // offsets (in floats) into the packed checkpoint, state_dict key order
 // MLP.{0,1,3,5,6,8,10,11,13}.{weight,bias} (obs_point_net.py:31-46); all multiples of 32.

@@ -34,6 +34,18 @@ struct DuneParams {
   int B, N, T, M;
   float dt;
   Geometry geo;
+  // screening (NB_OPT_DUNE_KERNEL = 4, dune_screen_kernel.cuh): candidate lists written by dune_screen_kernel, consumed by
+  // dune_refine_kernel; all nullptr / 0 in the other variants
+  int32_t* cand_idx;        // (B (T+1), 32) point indices
+  int32_t* cand_cnt;        // (B (T+1)): candidates of the item; -1 = evaluate the item exactly; 0 = nothing to do
+  float* cand_dt;           // (B (T+1), 32) screened distance of each candidate (NaN: not screened) -- statistics only
+  unsigned* screen_stats;   // [0] max |d~ - d| / sum|t| over candidates (float bits), [1] items sent to the exact kernel, [2] candidates, [3] items screened
+  float c_mu;               // bound on |mu~_e - mu_e| of the screening network
+  int32_t* flag_list;       // (B (T+1)) the items with cand_cnt == -1, in the order the screen kernel met them
+  int32_t* flag_count;      // (1) their number; zeroed by the launcher before the screen kernel
+  int only_flagged;         // exact kernel: process only the items of flag_list
+  int calibrate;            // screen kernel: items with N <= 32 are NOT short-cut: all their points become candidates with their screened
+                            // distance, so that the refine kernel's statistics compare the two networks on every point (nb_pan calibration)
 };
 
 __device__ __forceinline__ uint32_t orderable(float d) {

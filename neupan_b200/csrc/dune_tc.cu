@@ -7,6 +7,7 @@
 
 #include "dune_tc_kernel.cuh"
 #include "dune_tc8_kernel.cuh"
+#include "dune_screen_kernel.cuh"
 
 namespace nb {
 
@@ -20,7 +21,10 @@ static inline void split_half_tc(float v, uint16_t& hi, uint16_t& lo) {
 // packed checkpoint (WeightLayout order, E outputs) -> TcImage bytes (canonical K-major / no-swizzle UMMA layout)
 // returns flags: bit 0 = every tanh argument of the network is bounded by 30 in exp2 units (|LN(x)_j| <= sqrt(32)), which
 // allows the kernel's shared-reciprocal tanh (ln_tanh_split<true>)
-int build_tc_image(const float* w, int E, std::vector<unsigned char>& out) {
+// screen = true: the image of the screening network (dune_screen_kernel.cuh): the same layout, but tanh is NOT folded into the
+// following layer (the screen kernel applies MUFU.TANH itself) and the LayerNorm gain / offset are the checkpoint's plain values;
+// only the hi halves of the weights are used.
+int build_tc_image(const float* w, int E, std::vector<unsigned char>& out, bool screen) {
   using L = WeightLayout;
   using I = TcImage;
   out.assign(I::kBytes, 0);
@@ -33,7 +37,7 @@ int build_tc_image(const float* w, int E, std::vector<unsigned char>& out) {
   //   W tanh + b = (b + rowsum(W)) + (-2 W) r
   const int dense_w[5] = {L::W3, L::W5, L::W8, L::W10, L::W13}, dense_b[5] = {L::B3, L::B5, L::B8, L::B10, L::b13(E)};
   const int rows[5] = {32, 32, 32, 32, E};
-  const bool after_tanh[5] = {true, false, true, false, true};
+  const bool after_tanh[5] = {!screen, false, !screen, false, !screen};
   // Layers that feed a LayerNorm (MLP.0 -> LN1, MLP.5 -> LN6, MLP.10 -> LN11) are CENTRED here: LN subtracts the mean over
   // the 32 outputs, which is linear, so W - colmean(W) and b - mean(b) deliver mean-free pre-activations for free.
   const bool before_ln[5] = {false, true, false, true, false};
@@ -97,8 +101,9 @@ int build_tc_image(const float* w, int E, std::vector<unsigned char>& out) {
   const int g_dst[3] = {I::G1, I::G6, I::G11}, b_dst[3] = {I::BE1, I::BE6, I::BE11};
   for (int q = 0; q < 3; ++q)
     for (int i = 0; i < 32; ++i) {  // pre-multiplied by 2*log2(e): tanh(y) = 1 - 2/(exp2(2*log2(e)*y) + 1)
-      fl[g_dst[q] + i] = (float)((double)w[g_src[q] + i] * 2.8853900817779268);
-      fl[b_dst[q] + i] = (float)((double)w[b_src[q] + i] * 2.8853900817779268);
+      const double sc = screen ? 1.0 : 2.8853900817779268;
+      fl[g_dst[q] + i] = (float)((double)w[g_src[q] + i] * sc);
+      fl[b_dst[q] + i] = (float)((double)w[b_src[q] + i] * sc);
     }
   double amax = 0.0;
   for (int q = 0; q < 3; ++q)
@@ -109,8 +114,54 @@ int build_tc_image(const float* w, int E, std::vector<unsigned char>& out) {
   return amax <= 30.0 ? 1 : 0;
 }
 
-int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int image_flags, int variant, int sm_count, int max_smem_optin, cudaStream_t st, char* err,
-                   size_t errlen) {
+int launch_dune_tc(const DuneParams& prm_in, const unsigned char* d_image, const unsigned char* d_screen_image, int image_flags, int variant, int sm_count,
+                   int max_smem_optin, cudaStream_t st, char* err, size_t errlen) {
+  DuneParams prm = prm_in;
+  if (variant == 4) {
+    // screening: (1) interval pass over all points, (2) exact evaluation of the candidates, (3) the exact kernel for the items the
+    // screen could not narrow down to 32 candidates (below, with only_flagged)
+    if (!d_screen_image || !prm.cand_idx || !prm.cand_cnt || !prm.cand_dt || !prm.screen_stats || !prm.flag_list || !prm.flag_count) {
+      snprintf(err, errlen, "screening buffers are not allocated");
+      return -1;
+    }
+    const int items_ = prm.B * (prm.T + 1);
+    const size_t pad4 = (size_t)(233472 / 5) - 2048 + 512;  // never more than 4 CTAs (128 TMEM columns each) per SM
+    size_t smem_s = dune_screen_smem_bytes(prm.N, prm.M);
+    if ((long long)smem_s > max_smem_optin) {
+      snprintf(err, errlen, "N=%d needs %zu B of shared memory (limit %d)", prm.N, smem_s, max_smem_optin);
+      return -3;
+    }
+    if (smem_s < pad4) smem_s = pad4;
+    size_t smem_r = TcImage::kBytes + 64;
+    if (smem_r < pad4) smem_r = pad4;
+    int per_s = (int)(233472 / (smem_s + 2048));
+    per_s = per_s > 4 ? 4 : (per_s < 1 ? 1 : per_s);
+    cudaError_t e = cudaMemsetAsync(prm.flag_count, 0, sizeof(int32_t), st);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dune_screen_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+    if (e == cudaSuccess) {
+      int grid = sm_count * per_s;
+      if (grid > items_) grid = items_;
+      dune_screen_kernel<0><<<grid, 128, smem_s, st>>>(prm, d_screen_image);
+      e = cudaGetLastError();
+    }
+    const bool fast_r = (image_flags & 1) != 0;
+    if (e == cudaSuccess) e = fast_r ? cudaFuncSetAttribute(dune_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)
+                                      : cudaFuncSetAttribute(dune_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+    if (e == cudaSuccess) {
+      int grid = sm_count * 4;
+      const int groups = (items_ + 7) / 8;
+      if (grid > groups) grid = groups;
+      if (fast_r) dune_refine_kernel<true><<<grid, 128, smem_r, st>>>(prm, d_image);
+      else dune_refine_kernel<false><<<grid, 128, smem_r, st>>>(prm, d_image);
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "dune screen / refine launch failed: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    prm.only_flagged = 1;
+    variant = 2;
+  }
   size_t smem = variant == 3 ? dune_tc8_smem_bytes(prm.N, prm.geo.E, prm.M) : dune_tc_smem_bytes(prm.N, prm.geo.E, prm.M);
   if ((long long)smem > max_smem_optin) {
     snprintf(err, errlen, "N=%d needs %zu B of shared memory (limit %d)", prm.N, smem, max_smem_optin);

@@ -585,7 +585,9 @@ __global__ void __launch_bounds__(128, 4) dune_tcp_kernel(const DuneParams prm, 
 
   const int T1 = prm.T + 1, N = prm.N, M = prm.M, E = prm.geo.E;
   const int items = prm.B * T1;
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+  const int n_work = prm.only_flagged ? *prm.flag_count : items;  // screening mode: only the items the screen could not narrow down
+  for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    const int item = prm.only_flagged ? prm.flag_list[wi] : wi;
     const int b = item / T1, t = item - b * T1;
     if (prm.active && prm.active[b] == 0) continue;  // uniform per CTA
     int n = prm.num_points ? prm.num_points[b] : N;

@@ -24,9 +24,9 @@ void build_mma_image(const float* w, int E, std::vector<unsigned char>& out);
 int launch_dune_mma(const DuneParams& prm, const unsigned char* d_image, int sm_count, int max_smem_optin, int cta_per_sm_limit, cudaStream_t st,
                     char* err, size_t errlen);
 // dune_tc.cu
-int build_tc_image(const float* w, int E, std::vector<unsigned char>& out);
-int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, int image_flags, int variant, int sm_count, int max_smem_optin, cudaStream_t st, char* err,
-                   size_t errlen);
+int build_tc_image(const float* w, int E, std::vector<unsigned char>& out, bool screen);
+int launch_dune_tc(const DuneParams& prm, const unsigned char* d_image, const unsigned char* d_screen_image, int image_flags, int variant, int sm_count,
+                   int max_smem_optin, cudaStream_t st, char* err, size_t errlen);
 }  // namespace nb
 
 namespace {
@@ -88,6 +88,14 @@ struct nb_pan {
   unsigned char* d_image = nullptr;  // fragment-ordered fp16 hi/lo weight image of the mma.sync DUNE kernel
   unsigned char* d_tc_image = nullptr;  // UMMA operand image of the tcgen05 DUNE kernel
   int tc_flags = 0;                     // build_tc_image(): bit 0 = bounded tanh arguments
+  unsigned char* d_tc_screen = nullptr; // operand image of the screening network (NB_OPT_DUNE_KERNEL = 4)
+  int32_t *cand_idx = nullptr, *cand_cnt = nullptr, *flag_list = nullptr, *flag_count = nullptr;
+  float* cand_dt = nullptr;
+  unsigned* screen_stats = nullptr;
+  float c_mu = 0.012f;                  // bound on the screening network's |mu~ - mu|: set by calibrate_screen() to 4 x the largest error
+                                        // measured for THIS checkpoint and polygon (NB_SCREEN_CMU overrides)
+  bool screen_calibrated = false;
+  float screen_cal_ratio = 0.f;
   int dune_variant = 2;              // NB_OPT_DUNE_KERNEL: 0 = FP32 FFMA, 1 = mma.sync tensor-core, 2 = tcgen05 tensor-core kernel
   int overlap = 1;                   // NB_OPT_OVERLAP: number of env sub-batches pipelined on internal streams
   cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -135,9 +143,9 @@ int launch_dune(nb_pan* p, const nb::DuneParams& prm, cudaStream_t st, int cta_l
   int rc = NB_ERR_INVALID;
   char msg[256] = "";
   if (p->dune_variant >= 2) {
-    rc = nb::launch_dune_tc(prm, p->d_tc_image, p->tc_flags, p->dune_variant, p->sm_count, p->max_smem_optin, st, msg, sizeof(msg));
+    rc = nb::launch_dune_tc(prm, p->d_tc_image, p->d_tc_screen, p->tc_flags, p->dune_variant, p->sm_count, p->max_smem_optin, st, msg, sizeof(msg));
     if (rc) return fail(rc, "%s", msg);
-    ++g_launches;
+    g_launches += p->dune_variant == 4 ? 3 : 1;
     return NB_OK;
   }
   if (p->dune_variant == 1) {
@@ -237,6 +245,62 @@ int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st, int counter_slot
   return go(nb::nrmp_kernel<8, false, 0, 0>);
 }
 
+// Screening bound of this handle: the screen and the exact network evaluate the same 32-point items (points uniform in the square the
+// reference trains DUNE on, [-25, 25]^2, and in [-6, 6]^2 around the robot, identity frame) and the refine kernel's statistics give
+// max |d~ - d| / sum_e |G_e p - h_e| over every point; c_mu = 4 x that, clamped to [0.004, 0.05].
+int calibrate_screen(nb_pan* p, cudaStream_t st) {
+  const nb_pan_config& c = p->cfg;
+  const int T1 = c.receding + 1, N = 32;
+  int Bc = c.max_envs < 512 ? c.max_envs : 512;
+  const int rounds = (4096 + Bc * T1 - 1) / (Bc * T1) < 1 ? 1 : (4096 + Bc * T1 - 1) / (Bc * T1);
+  std::vector<float> pts((size_t)Bc * 2 * N), ns((size_t)Bc * 3 * T1, 0.f);
+  float *d_pts = nullptr, *d_ns = nullptr, *d_md = nullptr;
+  NB_CUDA(dalloc(&d_pts, pts.size()));
+  NB_CUDA(dalloc(&d_ns, ns.size()));
+  NB_CUDA(dalloc(&d_md, (size_t)Bc));
+  NB_CUDA(cudaMemcpyAsync(d_ns, ns.data(), ns.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  unsigned saved[4];
+  NB_CUDA(cudaStreamSynchronize(st));
+  NB_CUDA(cudaMemcpy(saved, p->screen_stats, sizeof(saved), cudaMemcpyDeviceToHost));
+  NB_CUDA(cudaMemset(p->screen_stats, 0, sizeof(saved)));
+  unsigned long long rng = 0x9E3779B97F4A7C15ull;
+  auto uni = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (float)((rng >> 40) * (1.0 / 16777216.0)); };
+  const int variant = p->dune_variant;
+  p->dune_variant = 4;
+  int rc = NB_OK;
+  for (int r = 0; r < (rounds > 16 ? 16 : rounds) && rc == NB_OK; ++r) {
+    for (int b = 0; b < Bc; ++b) {
+      const float R = ((b + r) & 1) ? 25.f : 6.f;
+      for (int i = 0; i < N; ++i) { pts[((size_t)b * 2) * N + i] = R * (2.f * uni() - 1.f); pts[((size_t)b * 2 + 1) * N + i] = R * (2.f * uni() - 1.f); }
+    }
+    cudaError_t e = cudaMemcpyAsync(d_pts, pts.data(), pts.size() * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = fail(NB_ERR_CUDA, "calibrate_screen: %s", cudaGetErrorString(e)); break; }
+    nb::DuneParams prm{};
+    prm.weights = p->d_weights; prm.nom_s = d_ns; prm.points = d_pts;
+    prm.sel_mu = p->sel_mu; prm.sel_lam = p->sel_lam; prm.sel_pts = p->sel_pts; prm.sel_dist = p->sel_dist; prm.sel_count = p->sel_count; prm.min_dist = d_md;
+    prm.B = Bc; prm.N = N; prm.T = c.receding; prm.M = c.nrmp_max_num; prm.dt = (float)c.step_time; prm.geo = p->geo;
+    prm.cand_idx = p->cand_idx; prm.cand_cnt = p->cand_cnt; prm.cand_dt = p->cand_dt; prm.screen_stats = p->screen_stats; prm.c_mu = p->c_mu;
+    prm.flag_list = p->flag_list; prm.flag_count = p->flag_count; prm.calibrate = 1;
+    rc = launch_dune(p, prm, st);
+    if (rc == NB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(NB_ERR_CUDA, "calibrate_screen: kernel failed");
+  }
+  p->dune_variant = variant;
+  if (rc == NB_OK) {
+    unsigned h[4];
+    NB_CUDA(cudaMemcpy(h, p->screen_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    float ratio;
+    memcpy(&ratio, &h[0], 4);
+    p->screen_cal_ratio = ratio;
+    float cm = 4.f * ratio;
+    p->c_mu = cm < 0.008f ? 0.008f : (cm > 0.05f ? 0.05f : cm);
+    if (const char* e = getenv("NB_SCREEN_CMU")) p->c_mu = (float)atof(e);
+    p->screen_calibrated = true;
+  }
+  cudaMemcpy(p->screen_stats, saved, sizeof(saved), cudaMemcpyHostToDevice);
+  cudaFree(d_pts); cudaFree(d_ns); cudaFree(d_md);
+  return rc;
+}
+
 __global__ void init_run_kernel(int B, int32_t* active, int32_t* iters, int32_t* status, float* min_dist, int32_t* sel_count, int32_t* warm_valid) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
@@ -308,9 +372,20 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
     nb::build_mma_image(weights, cfg->edge_dim, image);
     NB_CUDA(dalloc(&p->d_image, image.size()));
     NB_CUDA(cudaMemcpy(p->d_image, image.data(), image.size(), cudaMemcpyHostToDevice));
-    p->tc_flags = nb::build_tc_image(weights, cfg->edge_dim, image);
+    p->tc_flags = nb::build_tc_image(weights, cfg->edge_dim, image, false);
     NB_CUDA(dalloc(&p->d_tc_image, image.size()));
     NB_CUDA(cudaMemcpy(p->d_tc_image, image.data(), image.size(), cudaMemcpyHostToDevice));
+    nb::build_tc_image(weights, cfg->edge_dim, image, true);
+    NB_CUDA(dalloc(&p->d_tc_screen, image.size()));
+    NB_CUDA(cudaMemcpy(p->d_tc_screen, image.data(), image.size(), cudaMemcpyHostToDevice));
+    NB_CUDA(dalloc(&p->cand_idx, (size_t)cfg->max_envs * (cfg->receding + 1) * nb::kCandMax));
+    NB_CUDA(dalloc(&p->cand_dt, (size_t)cfg->max_envs * (cfg->receding + 1) * nb::kCandMax));
+    NB_CUDA(dalloc(&p->cand_cnt, (size_t)cfg->max_envs * (cfg->receding + 1)));
+    NB_CUDA(dalloc(&p->flag_list, (size_t)cfg->max_envs * (cfg->receding + 1)));
+    NB_CUDA(dalloc(&p->flag_count, (size_t)8));  // one counter per internal stream
+    NB_CUDA(dalloc(&p->screen_stats, (size_t)4));
+    NB_CUDA(cudaMemset(p->screen_stats, 0, 4 * sizeof(unsigned)));
+    if (const char* e = getenv("NB_SCREEN_CMU")) p->c_mu = (float)atof(e);
   }
   NB_CUDA(dalloc(&p->sel_mu, B * T1 * M * E));
   NB_CUDA(dalloc(&p->sel_lam, B * T1 * M * 2));
@@ -352,7 +427,7 @@ int nb_pan_destroy(nb_pan_t* p) {
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   void* bufs[] = {p->d_tc_image, p->d_image, p->d_weights, p->sel_mu, p->sel_lam, p->sel_pts, p->sel_dist, p->sel_count, p->prev_s, p->prev_u, p->prev_mu,
                   p->prev_lam, p->prev_count, p->prev_valid, p->active, p->iters, p->status, p->ipm_it, p->min_dist, p->h_in, p->h_out, p->h_np, p->h_io,
-                  p->warm, p->warm_valid, p->work_counters, p->adj_rec, p->adj_gs, p->adj_gu, p->adj_gd, p->adj_gtheta, p->adj_valid};
+                  p->d_tc_screen, p->cand_idx, p->cand_cnt, p->cand_dt, p->screen_stats, p->flag_list, p->flag_count, p->warm, p->warm_valid, p->work_counters, p->adj_rec, p->adj_gs, p->adj_gu, p->adj_gd, p->adj_gtheta, p->adj_valid};
   for (void* b : bufs)
     if (b) cudaFree(b);
   delete p;
@@ -375,8 +450,13 @@ int nb_pan_set_iteration(nb_pan_t* p, int32_t iter_num, float iter_threshold) {
 int nb_pan_set_option(nb_pan_t* p, int32_t option, int32_t value) {
   if (!p) return fail(NB_ERR_INVALID, "null handle");
   if (option == NB_OPT_DUNE_KERNEL) {
-    if (value < 0 || value > 3) return fail(NB_ERR_INVALID, "NB_OPT_DUNE_KERNEL takes 0 (fp32 ffma), 1 (mma.sync), 2 (tcgen05, thread per point) or 3 (tcgen05, two threads per point)");
+    if (value < 0 || value > 4)
+      return fail(NB_ERR_INVALID, "NB_OPT_DUNE_KERNEL takes 0 (fp32 ffma), 1 (mma.sync), 2 (tcgen05), 3 (tcgen05, two threads per point) or 4 (tcgen05 with screening)");
     p->dune_variant = value;
+    if (value == 4 && !p->screen_calibrated && p->d_tc_screen) {
+      NB_CUDA(cudaSetDevice(p->cfg.device));
+      return calibrate_screen(p, nullptr);
+    }
     return NB_OK;
   }
   if (option == NB_OPT_OVERLAP) {
@@ -430,6 +510,8 @@ int nb_dune_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const
   prm.sel_mu = p->sel_mu; prm.sel_lam = p->sel_lam; prm.sel_pts = p->sel_pts; prm.sel_dist = p->sel_dist; prm.sel_count = p->sel_count;
   prm.min_dist = out_min_distance;
   prm.B = B; prm.N = N; prm.T = p->cfg.receding; prm.M = p->cfg.nrmp_max_num; prm.dt = (float)p->cfg.step_time; prm.geo = p->geo;
+  prm.cand_idx = p->cand_idx; prm.cand_cnt = p->cand_cnt; prm.cand_dt = p->cand_dt; prm.screen_stats = p->screen_stats; prm.c_mu = p->c_mu;
+  prm.flag_list = p->flag_list; prm.flag_count = p->flag_count;
   return launch_dune(p, prm, (cudaStream_t)stream);
 }
 
@@ -494,6 +576,9 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
         d.sel_pts = p->sel_pts + (size_t)lo * T1s * Ms * 2; d.sel_dist = p->sel_dist + (size_t)lo * T1s * Ms; d.sel_count = p->sel_count + lo;
         d.min_dist = p->min_dist + lo;
         d.B = nb_; d.N = N; d.T = T; d.M = c.nrmp_max_num; d.dt = (float)c.step_time; d.geo = p->geo;
+        d.cand_idx = p->cand_idx + (size_t)lo * T1s * nb::kCandMax; d.cand_dt = p->cand_dt + (size_t)lo * T1s * nb::kCandMax;
+        d.cand_cnt = p->cand_cnt + (size_t)lo * T1s; d.screen_stats = p->screen_stats; d.c_mu = p->c_mu;
+        d.flag_list = p->flag_list + (size_t)lo * T1s; d.flag_count = p->flag_count + counter_slot;
         if (int rc = launch_dune(p, d, s, dune_cta_limit)) return rc;
       }
       nb::NrmpParams n{};
@@ -603,6 +688,21 @@ int nb_pan_read_selection(nb_pan_t* p, int32_t B, float* sel_mu, float* sel_lam,
   if (sel_points) NB_CUDA(cudaMemcpyAsync(sel_points, p->sel_pts, (size_t)B * T1 * M * 2 * 4, cudaMemcpyDeviceToDevice, st));
   if (sel_distance) NB_CUDA(cudaMemcpyAsync(sel_distance, p->sel_dist, (size_t)B * T1 * M * 4, cudaMemcpyDeviceToDevice, st));
   if (sel_count) NB_CUDA(cudaMemcpyAsync(sel_count, p->sel_count, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  return NB_OK;
+}
+
+int nb_pan_read_screen_stats(nb_pan_t* p, float* max_error_ratio, int32_t* counts, int32_t reset) {
+  if (!p || !max_error_ratio || !counts) return fail(NB_ERR_INVALID, "nb_pan_read_screen_stats: null argument");
+  if (!p->screen_stats) return fail(NB_ERR_INVALID, "handle was created in no_obs mode");
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  NB_CUDA(cudaDeviceSynchronize());
+  unsigned h[4];
+  NB_CUDA(cudaMemcpy(h, p->screen_stats, sizeof(h), cudaMemcpyDeviceToHost));
+  memcpy(max_error_ratio, &h[0], 4);
+  max_error_ratio[1] = p->c_mu;
+  max_error_ratio[2] = p->screen_cal_ratio;
+  counts[0] = (int32_t)h[1]; counts[1] = (int32_t)h[2]; counts[2] = (int32_t)h[3];
+  if (reset) NB_CUDA(cudaMemset(p->screen_stats, 0, sizeof(h)));
   return NB_OK;
 }
 

@@ -38,7 +38,7 @@ def _oracle_dune(cfg, inp, b):
 
 
 @pytest.mark.parametrize("cname", ["C1", "C2", "C3", "C4", "C5"])
-@pytest.mark.parametrize("dune_kernel", [3, 2, 1, 0])
+@pytest.mark.parametrize("dune_kernel", [4, 3, 2, 1, 0])
 def test_dune_half_matches_oracle(cname, dune_kernel):
     """DUNE kernel alone (tensor-core and all-FP32 variants): the M closest points per (env, step),
     their mu, lam, distance."""
