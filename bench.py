@@ -441,7 +441,8 @@ def run_ours(args):
                    sample=f"3 rounds x {summ['envs_per_round']} envs of {args.workload} (K={K}; 4 envs per worker process, {summ['cores']} processes, 1 thread each, "
                           f"warm-up = 1 env per worker), {summ['wall_s']:.1f} s wall; {CPU_WHAT}",
                    **{k: summ[k] for k in ("failed_envs", "highs_fallback_solves", "rate_per_round", "spread", "dune_ms_per_env", "nrmp_ms_per_env",
-                                            "pan_iterations_per_env", "env_steps_per_s_per_core", "rate_from_cpu_time")})
+                                            "pan_iterations_per_env", "env_steps_per_s_per_core", "rate_from_cpu_time", "logical_cpus", "affinity_cpus", "cgroup_quota_cores",
+                                            "effective_cores")})
 
     if rank == 0:
         value = world * B / (ms * 1e-3)
