@@ -436,9 +436,9 @@ def run_ours(args):
     # ---- cpu baseline (rank 0, N = 1 only), bounded sample ------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        summ, _ = cpu_sample(args.workload, K, args.iter_threshold, rounds=3, envs_per_worker=4)
+        summ, _ = cpu_sample(args.workload, K, args.iter_threshold, rounds=3, envs_per_worker=8)
         cpu = dict(value=summ["value"], unit=UNIT, cores=summ["cores"], kind="port",
-                   sample=f"3 rounds x {summ['envs_per_round']} envs of {args.workload} (K={K}; 4 envs per worker process, {summ['cores']} processes, 1 thread each, "
+                   sample=f"3 rounds x {summ['envs_per_round']} envs of {args.workload} (K={K}; 8 envs per worker process, {summ['cores']} processes, 1 thread each, "
                           f"warm-up = 1 env per worker), {summ['wall_s']:.1f} s wall; {CPU_WHAT}",
                    **{k: summ[k] for k in ("failed_envs", "highs_fallback_solves", "rate_per_round", "spread", "dune_ms_per_env", "nrmp_ms_per_env",
                                             "pan_iterations_per_env", "env_steps_per_s_per_core", "rate_from_cpu_time", "logical_cpus", "affinity_cpus", "cgroup_quota_cores",

@@ -81,6 +81,28 @@ __device__ __forceinline__ void relu_screen(const f2 (&hp)[16], uint32_t (&hi)[1
   }
 }
 
+// smallest value above k whose low 9 bits carry the point's index in the item (< 512): keys become unique, so a REDUX round
+// removes exactly one entry and needs no second reduction over indices.  Rounding a bound UP only widens the candidate set.
+__device__ __forceinline__ uint32_t unique_key(uint32_t k, int idx) { return ((min(k, 0xFFFFF000u) + 0x200u) & ~0x1FFu) | (uint32_t)idx; }
+
+// d~ = relu(mu)^T (G p0 - h) and sum_e |G_e p0 - h_e| (the factor of the error radius)
+template <int kE>
+__device__ __forceinline__ void screen_distance(const DuneParams& prm, const float (&mu)[8], float2 xy, int E, float& d, float& sa) {
+#pragma unroll
+  for (int e = 0; e < kE; ++e) {
+    if (e < E) {
+      const float ge = fmaf(prm.geo.G[e][1], xy.y, prm.geo.G[e][0] * xy.x) - prm.geo.h[e];
+      d = fmaf(fmaxf(mu[e], 0.f), ge, d);
+      sa += fabsf(ge);
+    }
+  }
+}
+
+__device__ __forceinline__ void cp_async4(const float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 }  // namespace tc
 
 // shared memory of the screen kernel: operand image | UB keys (N x 8) | lower bounds (N x 4) | d~ (N x 4) | per-warp candidates (4 M x 8)
@@ -148,15 +170,44 @@ __global__ void __launch_bounds__(128, 4) dune_screen_kernel(const DuneParams pr
 
   const int T1 = prm.T + 1, N = prm.N, M = prm.M, E = prm.geo.E;
   const int items = prm.B * T1;
+  // Items with n <= 512 keep their bounds in registers; the key arrays then stage the raw point data (x | y | vx | vy, N floats
+  // each), copied asynchronously (cp.async, each thread exactly the <= 4 entries it reads itself: no barrier) -- for the NEXT
+  // item as soon as the last stage 0 of the current one has consumed the buffer, so the point loads never sit on the critical path.
+  float* raw = reinterpret_cast<float*>(keys);
+  int staged = -1;  // item whose points are in (or on their way into) `raw`
+  auto stage_points = [&](int it) -> bool {
+    const int bb = it / T1;
+    int nn = prm.num_points ? prm.num_points[bb] : N;
+    nn = nn > N ? N : nn;
+    if ((nn <= kCandMax && !prm.calibrate) || nn > 512 || nn <= 0) return false;
+    const float* px = prm.points + (size_t)bb * 2 * N;
+    const float* vx = prm.velocities ? prm.velocities + (size_t)bb * 2 * N : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = tid + 128 * j;
+      if (i < nn) {
+        tc::cp_async4(raw + i, px + i);
+        tc::cp_async4(raw + N + i, px + N + i);
+        if (vx) {
+          tc::cp_async4(raw + 2 * N + i, vx + i);
+          tc::cp_async4(raw + 3 * N + i, vx + N + i);
+        }
+      }
+    }
+    return true;
+  };
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int b = item / T1, t = item - b * T1;
     int32_t* out_idx = prm.cand_idx + (size_t)item * kCandMax;
     float* out_dt = prm.cand_dt + (size_t)item * kCandMax;
-    if (prm.active && prm.active[b] == 0) {
+    // the item's header values are loaded together (one memory latency, not three dependent ones)
+    const int act = prm.active ? prm.active[b] : 1;
+    int n = prm.num_points ? prm.num_points[b] : N;
+    const tc::ItemFrame fr = tc::item_frame(prm, b, t);
+    if (act == 0) {
       if (tid == 0) prm.cand_cnt[item] = 0;
       continue;
     }
-    int n = prm.num_points ? prm.num_points[b] : N;
     n = n < 0 ? 0 : (n > N ? N : n);
     const int cnt = n < M ? n : M;
     if (t == 0 && tid == 0) {
@@ -168,8 +219,15 @@ __global__ void __launch_bounds__(128, 4) dune_screen_kernel(const DuneParams pr
       if (tid == 0) prm.cand_cnt[item] = n;
       continue;
     }
-    const tc::ItemFrame fr = tc::item_frame(prm, b, t);
     const bool reg_keys = n <= 512;  // the thread's (<= 4) bounds stay in registers; larger items use the shared-memory arrays
+    if (reg_keys) {
+      if (staged != item) {
+        tc::cp_async_wait_all();  // an abandoned copy (its item was skipped) must not land after this one
+        stage_points(item);
+        staged = item;
+      }
+      tc::cp_async_wait_all();
+    }
     uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu, k3 = 0xFFFFFFFFu;
     float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 
@@ -179,9 +237,19 @@ __global__ void __launch_bounds__(128, 4) dune_screen_kernel(const DuneParams pr
 #pragma unroll 1
       for (int sl = 0; sl < nslots; ++sl) {
         int i = base + sl * 128 + tid;
-        i = i < n ? i : n - 1;
-        float x0, y0;
-        fr.local(i, x0, y0);
+        float x0 = 0.f, y0 = 0.f;
+        if (!reg_keys) {
+          fr.local(i < n ? i : n - 1, x0, y0);
+        } else if (i < n) {  // rows beyond n run on zeros (their results are never looked at)
+          float gx = raw[i], gy = raw[N + i];
+          if (fr.vx) {
+            gx = flow(gx, raw[2 * N + i], fr.dt, fr.t);
+            gy = flow(gy, raw[3 * N + i], fr.dt, fr.t);
+          }
+          const float dx = gx - fr.sx, dy = gy - fr.sy;
+          x0 = fmaf(fr.cs, dx, fr.sn * dy);
+          y0 = fmaf(fr.cs, dy, -(fr.sn * dx));
+        }
         xy_s[sl][tid] = make_float2(x0, y0);
         const tc::f2 x2 = tc::pk(x0, x0), y2 = tc::pk(y0, y0);
         tc::f2 hp[16];
@@ -196,6 +264,9 @@ __global__ void __launch_bounds__(128, 4) dune_screen_kernel(const DuneParams pr
         uint32_t hi[16];
         tc::ln_tanh_screen(hp, fl + I::G1, fl + I::BE1, hi);
         publish(hi, sl, 0);
+      }
+      if (reg_keys && base + 256 >= n && item + (int)gridDim.x < items) {  // `raw` is free: start on the next item's points
+        if (stage_points(item + (int)gridDim.x)) staged = item + (int)gridDim.x;
       }
 #pragma unroll 1
       for (int st = 1; st < 5; ++st) {
@@ -221,16 +292,11 @@ __global__ void __launch_bounds__(128, 4) dune_screen_kernel(const DuneParams pr
         if (i < n) {
           const float2 xy = xy_s[sl][tid];
           float d = 0.f, sa = 0.f;
-#pragma unroll
-          for (int e = 0; e < kMaxEdges; ++e) {
-            if (e < E) {
-              const float ge = fmaf(prm.geo.G[e][1], xy.y, prm.geo.G[e][0] * xy.x) - prm.geo.h[e];
-              d = fmaf(fmaxf(mu[e], 0.f), ge, d);
-              sa += fabsf(ge);
-            }
-          }
+          if (E == 4) tc::screen_distance<4>(prm, mu, xy, 4, d, sa);  // every shipped robot: no per-edge branches
+          else tc::screen_distance<kMaxEdges>(prm, mu, xy, E, d, sa);
           const float eps = fmaf(prm.c_mu, sa, 1e-4f);
           kub = orderable(d + eps); lbi = d - eps; dti = d;
+          if (reg_keys) kub = tc::unique_key(kub, i);
           if (!reg_keys) {
             keys[i] = ((unsigned long long)kub << 32) | (unsigned)i;
             lbv[i] = lbi;
@@ -252,25 +318,34 @@ __global__ void __launch_bounds__(128, 4) dune_screen_kernel(const DuneParams pr
       __syncthreads();
       continue;
     }
-    // ---- tau = the M-th smallest upper bound: per-warp REDUX rounds (destroying the keys), then rank among the 4 M candidates
+    // ---- tau = the M-th smallest upper bound
+    uint32_t tau;
     if (reg_keys) {
-      unsigned long long* cand = cands + warp * M;
+      // unique 32-bit keys: M REDUX rounds per warp (each removes the one entry that equals the minimum), then every warp merges
+      // the 4 M survivors the same way -- no index reduction, no rank loop, no broadcast of tau through shared memory
+      uint32_t* c32 = reinterpret_cast<uint32_t*>(cands);
       uint32_t q0 = k0, q1 = k1, q2 = k2, q3 = k3;
       for (int m = 0; m < M; ++m) {
-        const uint32_t bd = min(min(q0, q1), min(q2, q3));
-        const uint32_t md = __reduce_min_sync(0xffffffffu, bd);
-        const int j = q0 == md ? 0 : (q1 == md ? 1 : (q2 == md ? 2 : 3));
-        const uint32_t bi = bd == md ? (uint32_t)(tid + 128 * j) : 0xFFFFFFFFu;
-        const uint32_t mi = __reduce_min_sync(0xffffffffu, bi);
-        if (md != 0xFFFFFFFFu && bi == mi) {
-          if (j == 0) q0 = 0xFFFFFFFFu;
-          else if (j == 1) q1 = 0xFFFFFFFFu;
-          else if (j == 2) q2 = 0xFFFFFFFFu;
-          else q3 = 0xFFFFFFFFu;
-        }
-        if (lane == 0) cand[m] = md == 0xFFFFFFFFu ? ~0ull : (((unsigned long long)md << 32) | mi);
+        const uint32_t md = __reduce_min_sync(0xffffffffu, min(min(q0, q1), min(q2, q3)));
+        q0 = q0 == md ? 0xFFFFFFFFu : q0; q1 = q1 == md ? 0xFFFFFFFFu : q1;
+        q2 = q2 == md ? 0xFFFFFFFFu : q2; q3 = q3 == md ? 0xFFFFFFFFu : q3;
+        if (lane == 0) c32[warp * M + m] = md;
       }
+      __syncthreads();
+      const int nc4 = 4 * M;  // <= 128 (M <= 32)
+      q0 = lane < nc4 ? c32[lane] : 0xFFFFFFFFu;
+      q1 = lane + 32 < nc4 ? c32[lane + 32] : 0xFFFFFFFFu;
+      q2 = lane + 64 < nc4 ? c32[lane + 64] : 0xFFFFFFFFu;
+      q3 = lane + 96 < nc4 ? c32[lane + 96] : 0xFFFFFFFFu;
+      uint32_t md = 0xFFFFFFFFu;
+      for (int m = 0; m < M; ++m) {  // n > kCandMax >= M: M finite keys exist
+        md = __reduce_min_sync(0xffffffffu, min(min(q0, q1), min(q2, q3)));
+        q0 = q0 == md ? 0xFFFFFFFFu : q0; q1 = q1 == md ? 0xFFFFFFFFu : q1;
+        q2 = q2 == md ? 0xFFFFFFFFu : q2; q3 = q3 == md ? 0xFFFFFFFFu : q3;
+      }
+      tau = md;
     } else {
+      // per-warp REDUX rounds over the keys in shared memory (destroying them), then rank among the 4 M candidates
       unsigned long long* cand = cands + warp * M;
       for (int m = 0; m < M; ++m) {
         unsigned bd = 0xFFFFFFFFu, bi = 0xFFFFFFFFu;
@@ -284,19 +359,19 @@ __global__ void __launch_bounds__(128, 4) dune_screen_kernel(const DuneParams pr
         if (lane == 0) cand[m] = md == 0xFFFFFFFFu ? ~0ull : (((unsigned long long)md << 32) | mi);
         __syncwarp();
       }
-    }
-    __syncthreads();
-    if (lane < M) {  // rank among the 4 M candidates (a ballot/popcount formulation over all lanes measured 8 % slower per launch)
-      const unsigned long long mine = cands[warp * M + lane];
-      int rank = lane;
-      for (int w = 0; w < 4; ++w) {
-        if (w == warp) continue;
-        for (int r = 0; r < M; ++r) rank += cands[w * M + r] < mine ? 1 : 0;
+      __syncthreads();
+      if (lane < M) {
+        const unsigned long long mine = cands[warp * M + lane];
+        int rank = lane;
+        for (int w = 0; w < 4; ++w) {
+          if (w == warp) continue;
+          for (int r = 0; r < M; ++r) rank += cands[w * M + r] < mine ? 1 : 0;
+        }
+        if (mine != ~0ull && rank == M - 1) tau_s = (uint32_t)(mine >> 32);  // n > kCandMax >= M: M finite keys exist
       }
-      if (mine != ~0ull && rank == M - 1) tau_s = (uint32_t)(mine >> 32);  // n > kCandMax >= M: M finite keys exist
+      __syncthreads();
+      tau = tau_s;
     }
-    __syncthreads();
-    const uint32_t tau = tau_s;
     if (reg_keys) {
       auto take = [&](uint32_t k, float lb, float dt, int j) {
         if (k != 0xFFFFFFFFu && orderable(lb) <= tau) {

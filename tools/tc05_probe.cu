@@ -3,6 +3,8 @@
 // nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tc05_probe tc05_probe.cu
 #include <cstdio>
 #include <cstdint>
+#include <cstring>
+#include <cmath>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -17,7 +19,11 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int max
   return false;
 }
 
+#ifdef PROBE_F16D
+constexpr uint32_t IDESC = (0u << 4) | (4u << 17) | (8u << 24);  // D=f16 (accumulators packed?), A=B=f16, K-major both, N=32, M=128
+#else
 constexpr uint32_t IDESC = (1u << 4) | (4u << 17) | (8u << 24);  // D=f32, A=B=f16, K-major both, N=32, M=128
+#endif
 
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
   // K-major, SWIZZLE_NONE: core matrix = 8 rows (N) x 16 B (8 halves of K), 128 B contiguous;
@@ -119,6 +125,18 @@ int main() {
   double maxerr = 0; int bad = 0;
   for (int i = 0; i < 128 * 32; ++i) { double d = fabs(hD[i] - ref[i]); if (d > maxerr) maxerr = d; if (d > 1e-3) ++bad; }
   printf("max err %.3e, mismatches %d / %d\n", maxerr, bad, 128 * 32);
+#ifdef PROBE_F16D
+  // raw dump: every 32-bit TMEM column of rows 5 and 100 as two halves, next to the reference row
+  for (int row : {5, 100}) {
+    printf("row %d raw columns (lo half, hi half):\n", row);
+    for (int c = 0; c < 32; ++c) {
+      uint32_t w; memcpy(&w, &hD[row * 32 + c], 4);
+      __half lo, hi; uint16_t l16 = w & 0xffff, h16 = w >> 16; memcpy(&lo, &l16, 2); memcpy(&hi, &h16, 2);
+      printf("  col %2d: %9.4f %9.4f   ref[%2d] = %9.4f\n", c, __half2float(lo), __half2float(hi), c, ref[row * 32 + c]);
+    }
+  }
+  return 0;
+#endif
   printf("D[0][0..3] = %f %f %f %f   ref %f %f %f %f\n", hD[0], hD[1], hD[2], hD[3], ref[0], ref[1], ref[2], ref[3]);
   printf("D[5][0..3] = %f %f %f %f   ref %f %f %f %f\n", hD[160], hD[161], hD[162], hD[163], ref[160], ref[161], ref[162], ref[163]);
   printf("D[100][28..31] = %f %f %f %f   ref %f %f %f %f\n", hD[3228], hD[3229], hD[3230], hD[3231], ref[3228], ref[3229], ref[3230], ref[3231]);
