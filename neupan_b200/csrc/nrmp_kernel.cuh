@@ -54,6 +54,7 @@ struct NrmpParams {
   // warm start (NB_OPT_NRMP_WARM): per-env float record [x (2T) | D (T) | z of the box/rate/D rows (mb) | z of the hinge rows (T*M)]
   // of the last converged solve; warm_valid[b] != 0 marks it usable.  nullptr = always cold.
   float* warm; int32_t* warm_valid;
+  int warm_check_it; double warm_check_gap;  // a warm start whose gap is still above warm_check_gap at iteration warm_check_it restarts cold
   int* work_counter;  // dynamic env -> warp assignment (see nrmp_kernel), or nullptr
   // differentiable mode (LON): per-env record of this solve for nrmp_adjoint_kernel, nrmp_adj_doubles(T, M)
   // doubles each, and a validity flag; nullptr = inference
@@ -511,7 +512,7 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
       if (finishing && prm.adj_save == nullptr) { converged = true; break; }
       // a warm start that is not well on its way by iteration 12 (gap still above 1e-5; a healthy one is below 1e-8 there) is
       // abandoned for a cold start -- rare (<1 % on C4), but one 60-iteration straggler would set the duration of the launch
-      if (warm && it == 12 && gap > 1e-5) { restart = true; break; }
+      if (warm && ((it == 12 && gap > 1e-5) || (it == prm.warm_check_it && gap > prm.warm_check_gap))) { restart = true; break; }
       accept_gap = gap < 1e-9 && res < 10.0 * res_tol;  // good enough to keep if the next factorisation fails in rounding noise
 
       // (b) barrier weights; hinge rows publish omega for the per-step reductions

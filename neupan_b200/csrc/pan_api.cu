@@ -115,6 +115,8 @@ struct nb_pan {
   int32_t* warm_valid = nullptr;
   int nrmp_warm = 0;                // NB_OPT_NRMP_WARM (off by default: see DESIGN.md 3.2)
   double nrmp_gap_tol = 1e-12;      // NB_NRMP_GAP_TOL (developer switch, read once at create)
+  int warm_check_it = 12;           // NB_NRMP_RESTART_IT / NB_NRMP_RESTART_GAP (developer switches): early cold restart of a warm start
+  double warm_check_gap = 1e-5;
   // staging for the host-pointer entry point
   float *h_in = nullptr, *h_out = nullptr;  // device staging
   size_t h_in_floats = 0, h_out_floats = 0;
@@ -191,6 +193,7 @@ int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st, int counter_slot
   prm.T = c.receding; prm.M = c.nrmp_max_num; prm.E = c.edge_dim; prm.kin = c.kinematics;
   prm.max_ipm_iter = 60;
   prm.gap_tol = p->nrmp_gap_tol;
+  prm.warm_check_it = p->warm_check_it; prm.warm_check_gap = p->warm_check_gap;
   prm.iter_threshold = c.iter_threshold;
   prm.dt = c.step_time; prm.L = c.wheelbase;
   for (int i = 0; i < 3; ++i) prm.q[i] = c.q_s[i];
@@ -408,6 +411,8 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
   NB_CUDA(dalloc(&p->warm_valid, B));
   NB_CUDA(dalloc(&p->work_counters, (size_t)8));
   if (getenv("NB_NRMP_STATIC")) p->nrmp_dynamic = 0;
+  if (const char* e = getenv("NB_NRMP_RESTART_IT")) p->warm_check_it = atoi(e);
+  if (const char* e = getenv("NB_NRMP_RESTART_GAP")) p->warm_check_gap = atof(e);
   NB_CUDA(cudaMemset(p->warm_valid, 0, B * sizeof(int32_t)));
   if (const char* e = getenv("NB_NRMP_GAP_TOL")) p->nrmp_gap_tol = atof(e);
   NB_CUDA(cudaMemset(p->prev_valid, 0, B * sizeof(int32_t)));
