@@ -146,6 +146,10 @@ __device__ __forceinline__ double rsqrt64(double x) {
   for (int i = 0; i < 2; ++i) r = r * fma(hx, r * r, 1.5);
   return r;
 }
+// D (8x8, FP64) += A (8x4, row) * B (4x8, col) on the FP64 tensor pipe.  Lane l = 4 g + q holds A[g][q], B[q][g], D[g][2q], D[g][2q+1].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 __device__ __forceinline__ float rcpf(double x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)x));
@@ -168,6 +172,10 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
   const int oBU = 0, oBL = nU, oRU = 2 * nU, oRL = oRU + nR, oDU = oRL + nR, oDL = oDU + TD;
   const int mb = oDL + TD;
   auto hrow = [](int i) { return (i * (i + 3)) >> 1; };  // offset of row i of the lower-triangular H / L
+#ifndef NB_NRMP_DMMA
+#define NB_NRMP_DMMA 1
+#endif
+  const bool kDmma = NB_NRMP_DMMA != 0 && SMALL && TD > 0;  // Hessian assembly on the FP64 tensor pipe (2T <= 32, obstacles present)
 
   // ---- carve this warp's workspace -------------------------------------------------------
   const int FT = T * (T + 1);                      // packed size of one component of F / G
@@ -553,9 +561,74 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
         const double hdd = nn + cz[oDU + t] * (double)cis[oDU + t] + cz[oDL + t] * (double)cis[oDL + t];
         const double ih = dfix ? 0.0 : rcp64(hdd);  // fixed D: no D block, dD = 0
         iHDD[t] = ih; n0[t] = b0; n1[t] = b1;
-        N00[t] = a00 - b0 * b0 * ih; N01[t] = a01 - b0 * b1 * ih; N11[t] = a11 - b1 * b1 * ih;
+        const double m00 = a00 - b0 * b0 * ih, m01 = a01 - b0 * b1 * ih, m11 = a11 - b1 * b1 * ih;
+        if (kDmma) {
+          // N_t = R'R (2x2 Cholesky; N_t is positive semidefinite by Cauchy-Schwarz, hdd >= sum omega): the Hessian update
+          // sum_t F_t' N_t F_t becomes V'V with V_t = R_t F_t, a plain Gram matrix for the tensor pipe
+          double r00 = 0.0, r01 = 0.0, r11 = 0.0;
+          if (m00 > 1e-30) { const double ir = rsqrt64(m00); r00 = m00 * ir; r01 = m01 * ir; }
+          const double v = fma(-r01, r01, m11);
+          if (v > 1e-30) r11 = v * rsqrt64(v);
+          N00[t] = r00; N01[t] = r01; N11[t] = r11;
+        } else {
+          N00[t] = m00; N01[t] = m01; N11[t] = m11;
+        }
       }
       __syncwarp();
+      if (kDmma) {
+        // V (packed like F, in the Gx | Gy scratch): row 2t = r00 Fx_t + r01 Fy_t, row 2t+1 = r11 Fy_t
+        NB_LL(j, nU) {
+          int o = (j >> 1) * ((j >> 1) + 1) + j;
+#pragma unroll 2
+          for (int t = j >> 1; t < T; ++t) {
+            const double fx = F[o], fy = F[FT + o];
+            Gx[o] = N00[t] * fx + N01[t] * fy;
+            Gy[o] = N11[t] * fy;
+            o += 2 * (t + 1);
+          }
+        }
+        __syncwarp();
+        // (c) reduced Hessian = Hc + V'V + bound terms: 8x8 tiles of the lower triangle on the FP64 tensor pipe (DMMA m8n8k4),
+        //     k-steps whose four rows of V are structurally zero in the tile's columns are skipped (T = 10: 14 DMMAs)
+        const int q = lane & 3, g = lane >> 2;
+        const int nT = (nU + 7) >> 3;
+#pragma unroll
+        for (int I = 0; I < (TT > 0 ? (2 * TT + 7) / 8 : 4); ++I) {
+          if (I >= nT) break;
+          const int i0 = 8 * I, ia = i0 + g;
+#pragma unroll
+          for (int J = 0; J <= I; ++J) {
+            const int j0 = 8 * J, jb = j0 + g;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int k0 = 0; k0 < (TT > 0 ? 2 * TT : 32); k0 += 4) {
+              if (k0 >= nU) break;
+              if (2 * (((k0 + 3) >> 1) + 1) <= i0) continue;  // rows k0..k0+3 have no entries in columns >= i0
+              const int k = k0 + q, t = k >> 1;
+              const int lim = k < nU ? 2 * t + 2 : 0;  // row k = 2t + c of V has columns [0, 2t + 2)
+              const double* vr = Gx + (k & 1) * FT + t * (t + 1);
+              const double a = ia < lim ? vr[ia] : 0.0;
+              const double b = I == J ? a : (jb < lim ? vr[jb] : 0.0);
+              dmma884(c0, c1, a, b);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = ia, j = j0 + 2 * q + e;
+              if (i < nU && j <= i) {
+                double acc = Hc[(i * (i + 1) >> 1) + j] + (e ? c1 : c0);
+                if (i == j) {
+                  acc += cz[oBU + i] * (double)cis[oBU + i] + cz[oBL + i] * (double)cis[oBL + i];
+                  if (i >= 2) acc += cz[oRU + i - 2] * (double)cis[oRU + i - 2] + cz[oRL + i - 2] * (double)cis[oRL + i - 2];
+                  if (i < nR) acc += cz[oRU + i] * (double)cis[oRU + i] + cz[oRL + i] * (double)cis[oRL + i];
+                } else if (i == j + 2) {
+                  acc -= cz[oRU + j] * (double)cis[oRU + j] + cz[oRL + j] * (double)cis[oRL + j];
+                }
+                H[hrow(i) + j] = acc;
+              }
+            }
+          }
+        }
+      } else {
       if (TD > 0) {
         NB_LL(j, nU) {
           int o = (j >> 1) * ((j >> 1) + 1) + j;
@@ -592,6 +665,7 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
           acc -= cz[oRU + j] * (double)cis[oRU + j] + cz[oRL + j] * (double)cis[oRL + j];
         }
         H[hrow(i) + j] = acc;
+      }
       }
       __syncwarp();
       // (d) Cholesky, left-looking; lane owns rows lane, lane+32; inverse diagonal in registers.
