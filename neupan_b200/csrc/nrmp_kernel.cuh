@@ -175,6 +175,14 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
 #ifndef NB_NRMP_DMMA
 #define NB_NRMP_DMMA 1
 #endif
+#ifndef NB_NRMP_UNROLL_CHOL
+#define NB_NRMP_UNROLL_CHOL 0
+#endif
+#ifndef NB_NRMP_UNROLL_SOLVE
+#define NB_NRMP_UNROLL_SOLVE 1
+#endif
+  constexpr int kUnrollSolve = (TT > 0 && NB_NRMP_UNROLL_SOLVE) ? 32 : 2;
+  constexpr int kUnrollCholK = (TT > 0 && NB_NRMP_UNROLL_CHOL) ? 16 : 1, kUnrollCholP = (TT > 0 && NB_NRMP_UNROLL_CHOL) ? 32 : 4;
   const bool kDmma = NB_NRMP_DMMA != 0 && SMALL && TD > 0;  // Hessian assembly on the FP64 tensor pipe (2T <= 32, obstacles present)
 
   // ---- carve this warp's workspace -------------------------------------------------------
@@ -674,7 +682,7 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
       bool bad = false;
       invd0 = 0.0; invd1 = 0.0;
       if (SMALL) {
-#pragma unroll 1
+#pragma unroll(kUnrollCholK)
         for (int k = 0; k < nU; k += 2) {
           const double* rowk = H + hrow(k);
           const double* rowk1 = H + hrow(k + 1);
@@ -684,7 +692,7 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
             const double* rowi = H + hrow(lane);
             a0 = rowi[k];
             if (in1) a1 = rowi[k + 1];
-#pragma unroll 4
+#pragma unroll(kUnrollCholP)
             for (int p = 0; p < k; ++p) {
               const double v = rowi[p];
               a0 -= v * rowk[p];
@@ -796,20 +804,22 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
           }
         }
         if (SMALL) {
-          const double* rowl = H + hrow(lane);  // L[lane][k], k < lane
-#pragma unroll 2
+          // r0 stays the running residual of this lane's row (no select per step: row k is final when step k reads it), the
+          // scaling by 1 / L_kk rides on the broadcast; with compile-time T both loops unroll into shuffle + predicated FMA
+          const double* rowl = H + hrow(lane < nU ? lane : 0);  // L[lane][k], k < lane (idle lanes read row 0, results unused)
+#pragma unroll(kUnrollSolve)
           for (int k = 0; k < nU; ++k) {
             const double yk = __shfl_sync(0xffffffffu, r0 * invd0, k);
-            if (lane == k) r0 = yk;
-            if (lane > k && lane < nU) r0 -= rowl[k] * yk;
+            if (lane > k) r0 = fma(-rowl[k], yk, r0);
           }
+          r0 *= invd0;  // y = L^-1 b
           const double* coll = H + lane;  // L[k][lane], k > lane
-#pragma unroll 2
+#pragma unroll(kUnrollSolve)
           for (int k = nU - 1; k >= 0; --k) {
             const double xk = __shfl_sync(0xffffffffu, r0 * invd0, k);
-            if (lane == k) r0 = xk;
-            if (lane < k) r0 -= coll[hrow(k)] * xk;
+            if (lane < k) r0 = fma(-coll[hrow(k)], xk, r0);
           }
+          r0 *= invd0;  // x = L^-T y
         } else {
 #pragma unroll 1
           for (int k = 0; k < nU; ++k) {
@@ -1187,16 +1197,19 @@ __global__ void __launch_bounds__((TT == 10 && MM == 10) ? 32 * NB_NRMP_WPC : 64
   }
   __syncthreads();
   double* wsp = smem_d + (size_t)warp * warp_doubles;
-  if (prm.work_counter == nullptr) {
-    const int b = blockIdx.x * warps_per_cta + warp;
-    if (b < prm.B && !(prm.active && prm.active[b] == 0)) nrmp_solve_env<HPL, SMALL, TT, MM>(prm, b, wsp, ptab, lane);
-    return;
-  }
+  // one call site (one inlined copy of the solve: the code is ~60 KB): without a counter the loop body runs once for the warp's own env
+  bool first = true;
 #pragma unroll 1
   for (;;) {
     int b = 0;
-    if (lane == 0) b = atomicAdd(prm.work_counter, 1);
-    b = __shfl_sync(0xffffffffu, b, 0);
+    if (prm.work_counter != nullptr) {
+      if (lane == 0) b = atomicAdd(prm.work_counter, 1);
+      b = __shfl_sync(0xffffffffu, b, 0);
+    } else {
+      if (!first) break;
+      first = false;
+      b = blockIdx.x * warps_per_cta + warp;
+    }
     if (b >= prm.B) break;
     if (prm.active && prm.active[b] == 0) continue;
     nrmp_solve_env<HPL, SMALL, TT, MM>(prm, b, wsp, ptab, lane);
