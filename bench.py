@@ -379,9 +379,9 @@ def run_ours(args):
         if args.dune_kernel == 4:
             tiles = B * (T + 1) * ((N + 127) // 128)
             exec_flops = tiles * 5 * 3 * 2.0 * 128 * 32 * 16  # screening pass: bias product + one fp16 pass (2 UMMA 128x32x16) per layer; + ~7 % for the refined candidates
-            kname = ("dune_screen_kernel + dune_refine_kernel + dune_tcp_kernel (tcgen05.mma kind::f16: single-pass fp16 interval screening of all points, "
-                     "fp16 hi/lo 3-pass exact network for the <= 32 candidates per item, full kernel for the items the screen cannot narrow down; "
-                     "bit-identical selection to the full kernel; SASS UTCHMMA / LDTM / STTM / MUFU.TANH)")
+            kname = ("dune_screen_mma_kernel + dune_refine_kernel + dune_tcp_kernel (single-pass fp16 interval screening of all points on mma.sync m16n8k16 with "
+                     "the activations in registers; tcgen05.mma kind::f16 fp16 hi/lo 3-pass exact network for the <= 32 candidates per item and the full kernel "
+                     "for the items the screen cannot narrow down; bit-identical selection to the full kernel; SASS HMMA.16816 / MUFU.TANH, UTCHMMA / LDTM / STTM)")
         elif args.dune_kernel == 3:
             tiles = B * (T + 1) * ((N + 127) // 128)
             exec_flops = tiles * 5 * 7 * 2.0 * 128 * 32 * 16
@@ -399,11 +399,13 @@ def run_ours(args):
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.workload)
         roof = dict(bound="tensor", achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"], traffic=traffic,
-                    kernel=kname, kernel_ms=dune_ms, share_of_step=iters_mean * dune_ms / ms, peak_source=pk["which"],
+                    kernel=kname, kernel_ms=dune_ms,
+                    # a full launch (all T+1 steps) is timed; inside a control step the launches of PAN iterations k > 0 skip the step-0 items
+                    share_of_step=(1.0 + max(0.0, iters_mean - 1.0) * (T / (T + 1.0) if args.dune_kernel == 4 else 1.0)) * dune_ms / ms, peak_source=pk["which"],
                     algorithmic_flops_per_launch=flops, tensor_executed_tflops=exec_flops / (dune_ms * 1e-3) / 1e12,
                     algorithmic_bytes_per_launch=alg_bytes, hbm_gbs_if_bytes_only=alg_bytes / (dune_ms * 1e-3) / 1e9, hbm_peak_gbs=pk["hbm_gbs"],
                     note="compute-bound path (SURVEY 8d): HBM < 1% utilised; the GEMMs are 32-wide slices between per-point LayerNorm/tanh, "
-                         "so the kernel is bound by instruction issue and the MUFU pipe (2 MUFU per tanh), not by the tensor pipe -- DESIGN.md 3.1")
+                         "so the kernel is bound by instruction issue / dependent-issue latency and the MUFU pipe, not by the tensor pipe -- DESIGN.md 3.1")
     hb.close()
     del hb, pan, dsets
 

@@ -126,8 +126,14 @@ int nb_pan_set_iteration(nb_pan_t* pan, int32_t iter_num, float iter_threshold);
  * per (environment, step) that can be among the M closest, the exact kernel for the items the screen cannot narrow down -- the same
  * selection and values as 2, bit for bit (csrc/dune_screen_kernel.cuh).
  * NB_OPT_DIFFERENTIABLE: 1 = every NRMP solve of nb_pan_forward also stores what nb_pan_backward needs (one extra factorisation
- * at the optimum + ~5 KB per environment and iteration); 0 (default) = inference only. */
-enum { NB_OPT_DUNE_KERNEL = 1, NB_OPT_OVERLAP = 2, NB_OPT_NRMP_WARM = 3, NB_OPT_DIFFERENTIABLE = 4 };
+ * at the optimum + ~5 KB per environment and iteration); 0 (default) = inference only.
+ * NB_OPT_DUNE_SCREEN_MMA (with NB_OPT_DUNE_KERNEL = 4): 1 (default) = the screening pass runs on warp-level mma.sync with the
+ * activations in registers (csrc/dune_screen_mma_kernel.cuh; clouds of at most 512 points, larger ones take the tcgen05 pass), 0 = on
+ * tcgen05 (csrc/dune_screen_kernel.cuh).  Same candidate contract, same final results (the refine / exact kernels are tcgen05 either way).
+ * NB_OPT_DUNE_SKIP_T0 (with NB_OPT_DUNE_KERNEL = 4): 1 (default) = PAN iterations k > 0 of one nb_pan_forward do not re-evaluate the
+ * step-0 items: nom_s[:, 0] is the fixed initial state (robot.py:234), so their inputs and results are those of iteration 0, which
+ * stand in the selection buffers; 0 = evaluate them in every iteration (identical results). */
+enum { NB_OPT_DUNE_KERNEL = 1, NB_OPT_OVERLAP = 2, NB_OPT_NRMP_WARM = 3, NB_OPT_DIFFERENTIABLE = 4, NB_OPT_DUNE_SCREEN_MMA = 5, NB_OPT_DUNE_SKIP_T0 = 6 };
 int nb_pan_set_option(nb_pan_t* pan, int32_t option, int32_t value);
 
 /* Replaces the backward pass of the reference's differentiable solve (CvxpyLayer, nrmp.py:144; used by LON,

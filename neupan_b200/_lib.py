@@ -21,6 +21,8 @@ OPT_DUNE_KERNEL = 1
 OPT_OVERLAP = 2
 OPT_NRMP_WARM = 3
 OPT_DIFFERENTIABLE = 4
+OPT_DUNE_SCREEN_MMA = 5
+OPT_DUNE_SKIP_T0 = 6
 
 
 class PanConfig(C.Structure):

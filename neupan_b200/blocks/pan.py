@@ -105,6 +105,10 @@ class PAN(torch.nn.Module):
         # 4 = tcgen05 with screening (default: bit-identical to 2, ~15 % less DUNE time), 2 = tcgen05 on every point, 3 = two threads per
         # point (experiment), 1 = mma.sync, 0 = all-FP32 FFMA
         self.dune_kernel = int(kwargs.get("dune_kernel", 4))
+        # with dune_kernel = 4: the screening pass on mma.sync (1, default; clouds of <= 512 points) or tcgen05 (0); PAN iterations k > 0
+        # keep the step-0 items of iteration 0 (1, default: nom_s[:, 0] is the fixed initial state) or re-evaluate them (0).  Same results.
+        self.dune_screen_mma = int(kwargs.get("dune_screen_mma", 1))
+        self.dune_skip_t0 = int(kwargs.get("dune_skip_t0", 1))
         self._cap = (max(1, int(kwargs.get("max_envs", 1))), max(1, int(kwargs.get("max_points", max(1, dune_max_num)))))
         self._forward_id = 0
         self._differentiable = None  # last NB_OPT_DIFFERENTIABLE value pushed to the handle
@@ -162,6 +166,8 @@ class PAN(torch.nn.Module):
         self._handle, self._cap = handle, (cap_b, cap_n)
         if not self.no_obs:
             _lib.check(lib.nb_pan_set_option(handle, _lib.OPT_DUNE_KERNEL, int(self.dune_kernel)))
+            _lib.check(lib.nb_pan_set_option(handle, _lib.OPT_DUNE_SCREEN_MMA, int(self.dune_screen_mma)))
+            _lib.check(lib.nb_pan_set_option(handle, _lib.OPT_DUNE_SKIP_T0, int(self.dune_skip_t0)))
         _lib.check(lib.nb_pan_set_option(handle, _lib.OPT_OVERLAP, int(self.overlap)))
         _lib.check(lib.nb_pan_set_option(handle, _lib.OPT_NRMP_WARM, int(self.nrmp_warm)))
         self._sent = (self.nrmp_layer.version, int(self.iter_num), float(self.iter_threshold))

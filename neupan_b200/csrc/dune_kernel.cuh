@@ -44,6 +44,10 @@ struct DuneParams {
   int32_t* flag_list;       // (B (T+1)) the items with cand_cnt == -1, in the order the screen kernel met them
   int32_t* flag_count;      // (1) their number; zeroed by the launcher before the screen kernel
   int only_flagged;         // exact kernel: process only the items of flag_list
+  int skip_t0;              // screen kernels: step-0 items are skipped (cand_cnt = 0) and keep the outputs of the previous launch -- set by
+                            // nb_pan_forward for PAN iterations k > 0: nom_s[:, 0] is the fixed initial state (robot.py:234; the NRMP kernel
+                            // copies the column bit for bit), so item (b, 0) has the same inputs and the same result in every iteration
+  int screen_mma;           // launcher hint (NB_OPT_DUNE_SCREEN_MMA): 1 = screening pass on mma.sync (dune_screen_mma_kernel.cuh) where N <= 512
   int calibrate;            // screen kernel: items with N <= 32 are NOT short-cut: all their points become candidates with their screened
                             // distance, so that the refine kernel's statistics compare the two networks on every point (nb_pan calibration)
 };

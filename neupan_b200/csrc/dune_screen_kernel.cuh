@@ -198,6 +198,10 @@ __global__ void __launch_bounds__(128, 4) dune_screen_kernel(const DuneParams pr
   };
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int b = item / T1, t = item - b * T1;
+    if (prm.skip_t0 && t == 0) {  // same inputs as in the previous PAN iteration: its outputs stand
+      if (tid == 0) prm.cand_cnt[item] = 0;
+      continue;
+    }
     int32_t* out_idx = prm.cand_idx + (size_t)item * kCandMax;
     float* out_dt = prm.cand_dt + (size_t)item * kCandMax;
     // the item's header values are loaded together (one memory latency, not three dependent ones)

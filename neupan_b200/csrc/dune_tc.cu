@@ -8,6 +8,7 @@
 #include "dune_tc_kernel.cuh"
 #include "dune_tc8_kernel.cuh"
 #include "dune_screen_kernel.cuh"
+#include "dune_screen_mma_kernel.cuh"
 
 namespace nb {
 
@@ -136,13 +137,33 @@ int launch_dune_tc(const DuneParams& prm_in, const unsigned char* d_image, const
     if (smem_r < pad4) smem_r = pad4;
     int per_s = (int)(233472 / (smem_s + 2048));
     per_s = per_s > 4 ? 4 : (per_s < 1 ? 1 : per_s);
+    const int screen_mma = prm.screen_mma;
     cudaError_t e = cudaMemsetAsync(prm.flag_count, 0, sizeof(int32_t), st);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dune_screen_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
-    if (e == cudaSuccess) {
-      int grid = sm_count * per_s;
-      if (grid > items_) grid = items_;
-      dune_screen_kernel<0><<<grid, 128, smem_s, st>>>(prm, d_screen_image);
-      e = cudaGetLastError();
+    const size_t smem_m = dune_screen_mma_smem_bytes(prm.N, prm.M);
+    if (screen_mma && prm.N <= 512 && (long long)smem_m <= max_smem_optin) {  // larger clouds: the tcgen05 screen kernel (key arrays in shared memory)
+      // no TMEM in this kernel: residency is whatever registers and shared memory admit
+      static int per_m = -1;
+      static size_t per_m_smem = 0;
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(dune_screen_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+      if (e == cudaSuccess && (per_m < 0 || per_m_smem != smem_m)) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_m, dune_screen_mma_kernel<0>, 128, smem_m);
+        per_m_smem = smem_m;
+        if (per_m < 1) per_m = 1;
+      }
+      if (e == cudaSuccess) {
+        int grid = sm_count * per_m;
+        if (grid > items_) grid = items_;
+        dune_screen_mma_kernel<0><<<grid, 128, smem_m, st>>>(prm, d_screen_image);
+        e = cudaGetLastError();
+      }
+    } else {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(dune_screen_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+      if (e == cudaSuccess) {
+        int grid = sm_count * per_s;
+        if (grid > items_) grid = items_;
+        dune_screen_kernel<0><<<grid, 128, smem_s, st>>>(prm, d_screen_image);
+        e = cudaGetLastError();
+      }
     }
     const bool fast_r = (image_flags & 1) != 0;
     if (e == cudaSuccess) e = fast_r ? cudaFuncSetAttribute(dune_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)

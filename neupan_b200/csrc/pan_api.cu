@@ -110,6 +110,8 @@ struct nb_pan {
   double *adj_rec = nullptr, *adj_gs = nullptr, *adj_gu = nullptr, *adj_gd = nullptr, *adj_gtheta = nullptr;
   int32_t* adj_valid = nullptr;
   int* work_counters = nullptr;     // dynamic env -> warp assignment of the NRMP kernel, one counter per internal stream
+  int dune_skip_t0 = 1;             // NB_OPT_DUNE_SKIP_T0: PAN iterations k > 0 keep the step-0 items of iteration 0 (screening variant)
+  int screen_mma = 1;               // NB_OPT_DUNE_SCREEN_MMA: screening pass on mma.sync (N <= 512) instead of tcgen05
   int nrmp_dynamic = 1;             // NB_NRMP_STATIC=1 (developer switch, read at create) turns the persistent-warp schedule off
   float* warm = nullptr;            // NRMP warm-start records, nrmp_warm_floats(T, M) per environment
   int32_t* warm_valid = nullptr;
@@ -284,8 +286,11 @@ int calibrate_screen(nb_pan* p, cudaStream_t st) {
     prm.B = Bc; prm.N = N; prm.T = c.receding; prm.M = c.nrmp_max_num; prm.dt = (float)c.step_time; prm.geo = p->geo;
     prm.cand_idx = p->cand_idx; prm.cand_cnt = p->cand_cnt; prm.cand_dt = p->cand_dt; prm.screen_stats = p->screen_stats; prm.c_mu = p->c_mu;
     prm.flag_list = p->flag_list; prm.flag_count = p->flag_count; prm.calibrate = 1;
-    rc = launch_dune(p, prm, st);
-    if (rc == NB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(NB_ERR_CUDA, "calibrate_screen: kernel failed");
+    for (int shape = 0; shape < 2 && rc == NB_OK; ++shape) {  // both screening kernels (tcgen05 / mma.sync): the bound holds whichever option is set later
+      prm.screen_mma = shape;
+      rc = launch_dune(p, prm, st);
+      if (rc == NB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(NB_ERR_CUDA, "calibrate_screen: kernel failed");
+    }
   }
   p->dune_variant = variant;
   if (rc == NB_OK) {
@@ -411,6 +416,8 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
   NB_CUDA(dalloc(&p->warm_valid, B));
   NB_CUDA(dalloc(&p->work_counters, (size_t)8));
   if (getenv("NB_NRMP_STATIC")) p->nrmp_dynamic = 0;
+  if (const char* e = getenv("NB_DUNE_SKIP_T0")) p->dune_skip_t0 = atoi(e) != 0;  // developer overrides of the option defaults
+  if (const char* e = getenv("NB_SCREEN_MMA")) p->screen_mma = atoi(e) != 0;
   if (const char* e = getenv("NB_NRMP_RESTART_IT")) p->warm_check_it = atoi(e);
   if (const char* e = getenv("NB_NRMP_RESTART_GAP")) p->warm_check_gap = atof(e);
   NB_CUDA(cudaMemset(p->warm_valid, 0, B * sizeof(int32_t)));
@@ -480,6 +487,11 @@ int nb_pan_set_option(nb_pan_t* p, int32_t option, int32_t value) {
     p->differentiable = value;
     return NB_OK;
   }
+  if (option == NB_OPT_DUNE_SCREEN_MMA || option == NB_OPT_DUNE_SKIP_T0) {
+    if (value < 0 || value > 1) return fail(NB_ERR_INVALID, "NB_OPT_DUNE_SCREEN_MMA / NB_OPT_DUNE_SKIP_T0 take 0 or 1");
+    (option == NB_OPT_DUNE_SCREEN_MMA ? p->screen_mma : p->dune_skip_t0) = value;
+    return NB_OK;
+  }
   if (option == NB_OPT_NRMP_WARM) {
     if (value < 0 || value > 1) return fail(NB_ERR_INVALID, "NB_OPT_NRMP_WARM takes 0 or 1");
     p->nrmp_warm = value;
@@ -516,7 +528,7 @@ int nb_dune_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const
   prm.min_dist = out_min_distance;
   prm.B = B; prm.N = N; prm.T = p->cfg.receding; prm.M = p->cfg.nrmp_max_num; prm.dt = (float)p->cfg.step_time; prm.geo = p->geo;
   prm.cand_idx = p->cand_idx; prm.cand_cnt = p->cand_cnt; prm.cand_dt = p->cand_dt; prm.screen_stats = p->screen_stats; prm.c_mu = p->c_mu;
-  prm.flag_list = p->flag_list; prm.flag_count = p->flag_count;
+  prm.flag_list = p->flag_list; prm.flag_count = p->flag_count; prm.screen_mma = p->screen_mma;
   return launch_dune(p, prm, (cudaStream_t)stream);
 }
 
@@ -584,6 +596,8 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
         d.cand_idx = p->cand_idx + (size_t)lo * T1s * nb::kCandMax; d.cand_dt = p->cand_dt + (size_t)lo * T1s * nb::kCandMax;
         d.cand_cnt = p->cand_cnt + (size_t)lo * T1s; d.screen_stats = p->screen_stats; d.c_mu = p->c_mu;
         d.flag_list = p->flag_list + (size_t)lo * T1s; d.flag_count = p->flag_count + counter_slot;
+        d.screen_mma = p->screen_mma;
+        d.skip_t0 = (k > 0 && p->dune_skip_t0) ? 1 : 0;  // the step-0 items of iteration 0 stand (DuneParams::skip_t0)
         if (int rc = launch_dune(p, d, s, dune_cta_limit)) return rc;
       }
       nb::NrmpParams n{};

@@ -6,11 +6,11 @@ from helpers import CONFIGS, weights_path
 from neupan_b200 import PAN
 
 
-def make_pan(cfg, K=None, iter_threshold=0.0, N=None, adjust=None, M=None, max_envs=1, dune_max_num=None, dune_kernel=4, overlap=1, nrmp_warm=0):
+def make_pan(cfg, K=None, iter_threshold=0.0, N=None, adjust=None, M=None, max_envs=1, dune_max_num=None, dune_kernel=4, overlap=1, nrmp_warm=0, **pan_kw):
     rb = cfg.make_robot()
     return PAN(cfg.T, cfg.dt, rb, iter_num=cfg.K if K is None else K, dune_max_num=(cfg.N if N is None else N) if dune_max_num is None else dune_max_num,
                nrmp_max_num=cfg.M if M is None else M, dune_checkpoint=weights_path(cfg.model), iter_threshold=iter_threshold,
-               adjust_kwargs=dict(adjust or cfg.adjust), max_envs=max_envs, max_points=cfg.N if N is None else N, dune_kernel=dune_kernel, overlap=overlap, nrmp_warm=nrmp_warm)
+               adjust_kwargs=dict(adjust or cfg.adjust), max_envs=max_envs, max_points=cfg.N if N is None else N, dune_kernel=dune_kernel, overlap=overlap, nrmp_warm=nrmp_warm, **pan_kw)
 
 
 def to_cuda(inp):

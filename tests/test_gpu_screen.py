@@ -53,6 +53,18 @@ def test_screened_equals_full_kernel_bitwise(cname, scene):
     assert st["screened_items"] > 0
 
 
+@pytest.mark.parametrize("screen_mma,skip_t0", [(0, 0), (0, 1), (1, 0)])
+@pytest.mark.parametrize("cname", ["C2", "C4", "C5"])
+def test_screen_shapes_and_step0_reuse_equal_full_kernel_bitwise(cname, screen_mma, skip_t0):
+    """The non-default combinations of NB_OPT_DUNE_SCREEN_MMA (screening pass on tcgen05 / mma.sync) and NB_OPT_DUNE_SKIP_T0 (step-0
+    items of PAN iterations k > 0 re-evaluated / kept): same bits as the full kernel, like the defaults in the tests above."""
+    cfg = CONFIGS[cname]
+    inp = make_inputs(cfg, B=12 if cname != "C5" else 6, scene="obstacles" if cname == "C2" else "annulus")
+    full, scr = _pair(cfg, inp, 3, dune_screen_mma=screen_mma, dune_skip_t0=skip_t0)
+    _assert_equal(full, scr)
+    assert scr[5].screen_stats()["screened_items"] > 0
+
+
 def test_full_size_c4_bitwise_and_statistics():
     cfg = CONFIGS["C4"]
     inp = make_inputs(cfg, B=4096)
