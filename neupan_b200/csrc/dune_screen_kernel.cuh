@@ -98,6 +98,14 @@ __device__ __forceinline__ void screen_distance(const DuneParams& prm, const flo
   }
 }
 
+// one thread: item -> the refine list of its size class (dune_refine_kernel packs two items of <= 16 candidates into one warp)
+__device__ __forceinline__ void refine_append(const DuneParams& prm, int item, int nc) {
+  if (nc <= 0) return;
+  const int big = nc > 16 ? 1 : 0;
+  const int pos = atomicAdd(prm.flag_count + 1 + big, 1);
+  prm.refine_list[(size_t)big * prm.B * (prm.T + 1) + pos] = item;
+}
+
 __device__ __forceinline__ void cp_async4(const float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -220,7 +228,7 @@ __global__ void __launch_bounds__(128, 4) dune_screen_kernel(const DuneParams pr
     }
     if (n <= kCandMax && !prm.calibrate) {  // nothing to screen: every point is a candidate
       if (tid < n) { out_idx[tid] = tid; out_dt[tid] = __int_as_float(0x7fc00000); }
-      if (tid == 0) prm.cand_cnt[item] = n;
+      if (tid == 0) { prm.cand_cnt[item] = n; tc::refine_append(prm, item, n); }
       continue;
     }
     const bool reg_keys = n <= 512;  // the thread's (<= 4) bounds stay in registers; larger items use the shared-memory arrays
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(128, 4) dune_screen_kernel(const DuneParams pr
     __syncthreads();
     if (n <= kCandMax) {  // calibration mode: all points, with their screened distance
       if (tid < n) { out_idx[tid] = tid; out_dt[tid] = d0; }
-      if (tid == 0) prm.cand_cnt[item] = n;
+      if (tid == 0) { prm.cand_cnt[item] = n; tc::refine_append(prm, item, n); }
       __syncthreads();
       continue;
     }
@@ -398,6 +406,7 @@ __global__ void __launch_bounds__(128, 4) dune_screen_kernel(const DuneParams pr
       if (tid < nc) { out_idx[tid] = list_s[tid]; out_dt[tid] = ldt_s[tid]; }
       if (tid == 0) {
         prm.cand_cnt[item] = nc;
+        tc::refine_append(prm, item, nc);
         atomicAdd(&prm.screen_stats[2], (unsigned)nc);
         atomicAdd(&prm.screen_stats[3], 1u);
       }
@@ -415,7 +424,10 @@ __global__ void __launch_bounds__(128, 4) dune_screen_kernel(const DuneParams pr
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-// Exact evaluation of the candidates: 8 items per two-slot pass (slot s, warp w -> item 8 g + 4 s + w), lane = candidate.
+// Exact evaluation of the candidates.  Work units come from the two lists the screen kernels fill: an item with 17..32 candidates
+// takes a warp, two items with <= 16 candidates share one (lanes 0-15 / 16-31) -- the typical item has 11-16 candidates, so the
+// paired form nearly halves the number of 128-row tiles.  8 units per two-slot pass (slot s, warp w -> unit 8 g + 4 s + w), lane =
+// candidate.  Rows of an MMA tile are independent, so where a candidate sits does not change its mu / distance by a bit.
 template <bool kFast>
 __global__ void __launch_bounds__(128, 4) dune_refine_kernel(const DuneParams prm, const unsigned char* __restrict__ image) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -469,28 +481,31 @@ __global__ void __launch_bounds__(128, 4) dune_refine_kernel(const DuneParams pr
 
   const int T1 = prm.T + 1, M = prm.M, E = prm.geo.E;
   const int items = prm.B * T1;
-  const int groups = (items + 7) >> 3;
+  const int nA = prm.flag_count[1], nB = prm.flag_count[2];  // items with <= 16 / with 17..32 candidates
+  const int units = nB + ((nA + 1) >> 1);
+  const int groups = (units + 7) >> 3;
+  const int half = lane >> 4;
   for (int g = blockIdx.x; g < groups; g += gridDim.x) {
-    // does this group hold any work at all?  (uniform: all threads read the same 8 counts)
-    int any = 0;
-    for (int q = 0; q < 8; ++q) {
-      const int it = 8 * g + q;
-      any |= (it < items && prm.cand_cnt[it] > 0) ? 1 : 0;
-    }
-    if (!any) continue;
-    int myitem[2], mycnt[2], myidx[2];
+    int myitem[2], myidx[2], myli[2];  // the lane's item (-1: none), its point, its position in the item's candidate list (-1: not a candidate)
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl) {
-      const int it = 8 * g + 4 * sl + warp;
-      myitem[sl] = it;
-      int c = it < items ? prm.cand_cnt[it] : 0;
+      const int u = 8 * g + 4 * sl + warp;
+      int it = -1, li = lane;
+      if (u < nB) it = prm.refine_list[items + u];
+      else if (u < units) {
+        const int q = 2 * (u - nB) + half;
+        it = q < nA ? prm.refine_list[q] : -1;
+        li = lane & 15;
+      }
+      int c = it >= 0 ? prm.cand_cnt[it] : 0;
       c = c > 0 ? c : 0;
-      mycnt[sl] = c;
-      myidx[sl] = (c > 0) ? prm.cand_idx[(size_t)it * kCandMax + (lane < c ? lane : 0)] : 0;
+      myitem[sl] = it;
+      myli[sl] = li < c ? li : -1;
+      myidx[sl] = c > 0 ? prm.cand_idx[(size_t)it * kCandMax + (li < c ? li : 0)] : 0;  // idle rows run on a valid point of the item
     }
 #pragma unroll 1
     for (int sl = 0; sl < 2; ++sl) {  // stage 0
-      const int it = myitem[sl] < items ? myitem[sl] : items - 1;
+      const int it = myitem[sl] >= 0 ? myitem[sl] : 0;
       const tc::ItemFrame fr = tc::item_frame(prm, it / T1, it % T1);
       float x0, y0;
       fr.local(myidx[sl], x0, y0);
@@ -522,15 +537,16 @@ __global__ void __launch_bounds__(128, 4) dune_refine_kernel(const DuneParams pr
       }
     }
 #pragma unroll 1
-    for (int sl = 0; sl < 2; ++sl) {  // head, per-warp selection, output rows
+    for (int sl = 0; sl < 2; ++sl) {  // head, selection inside the lane's group (warp or half warp), output rows
       float mu[8];
       acquire(sl);
       tc::ld8(trow + 64 * sl, mu);
-      const int c = mycnt[sl];
-      if (c == 0) continue;  // warp-uniform
-      const int it = myitem[sl], b = it / T1, t = it - b * T1;
+      const int u = 8 * g + 4 * sl + warp;
+      if (u >= units) continue;  // warp-uniform
+      const bool whole = u < nB;  // warp-uniform
+      const bool valid = myli[sl] >= 0;
+      const int it = myitem[sl] >= 0 ? myitem[sl] : 0, b = it / T1, t = it - b * T1;
       const tc::ItemFrame fr = tc::item_frame(prm, b, t);
-      const bool valid = lane < c;
       const int idx = myidx[sl];
       float x0, y0;
       fr.local(idx, x0, y0);
@@ -544,10 +560,12 @@ __global__ void __launch_bounds__(128, 4) dune_refine_kernel(const DuneParams pr
           sa += fabsf(ge);
         }
       }
+      const unsigned gmask = whole ? 0xffffffffu : (half ? 0xffff0000u : 0x0000ffffu);
+      bool live = valid;
       {  // the screening error on the candidates (NaN marks unscreened items): statistics, and the run-time check of the bound --
          // a candidate whose screened distance is off by more than HALF its assumed radius sends the whole item to the exact kernel
          // (which runs after this one), so the selection never rests on an error bound that the item itself contradicts
-        const float dt = prm.cand_dt[(size_t)it * kCandMax + (valid ? lane : 0)];
+        const float dt = prm.cand_dt[(size_t)it * kCandMax + (valid ? myli[sl] : 0)];
         const bool screened = valid && dt == dt;
         const float err = screened ? fabsf(dt - d) : 0.f;
         float ratio = screened ? err / fmaxf(sa, 1e-6f) : 0.f;
@@ -555,28 +573,30 @@ __global__ void __launch_bounds__(128, 4) dune_refine_kernel(const DuneParams pr
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ratio = fmaxf(ratio, __shfl_xor_sync(0xffffffffu, ratio, o));
         if (lane == 0 && ratio > 0.f) atomicMax(&prm.screen_stats[0], __float_as_uint(ratio));
-        if (__any_sync(0xffffffffu, viol)) {  // warp-uniform
-          if (lane == 0) {
+        if ((__ballot_sync(0xffffffffu, viol) & gmask) != 0u) {  // uniform within the group
+          if (myli[sl] == 0) {
             prm.cand_cnt[it] = -1;
             atomicAdd(&prm.screen_stats[1], 1u);
             prm.flag_list[atomicAdd(prm.flag_count, 1)] = it;
           }
-          continue;
+          live = false;
         }
       }
-      const uint32_t key = valid ? orderable(d) : 0xFFFFFFFFu;
+      // rank of the lane's (distance, point index) among its group's candidates: ascending distance, ties -> lower point index,
+      // NaN distances last and never selected (like select_and_write_reg)
+      const uint32_t key = live ? orderable(d) : 0xFFFFFFFFu;
+      int rank = 0;
+      const int gbase = whole ? 0 : (lane & 16), gsz = whole ? 32 : 16;
+#pragma unroll 4
+      for (int j = 0; j < gsz; ++j) {
+        const uint32_t kj = __shfl_sync(0xffffffffu, key, gbase + j);
+        const int ij = __shfl_sync(0xffffffffu, idx, gbase + j);
+        rank += (kj < key || (kj == key && ij < idx)) ? 1 : 0;
+      }
       int n_b = prm.num_points ? prm.num_points[b] : prm.N;
       n_b = n_b < 0 ? 0 : (n_b > prm.N ? prm.N : n_b);
       const int cnt_out = n_b < M ? n_b : M;
-      bool alive = valid;
-      int rank = -1;
-      for (int m = 0; m < cnt_out; ++m) {  // ascending distance, ties -> lower point index (like select_and_write_reg)
-        const uint32_t md = __reduce_min_sync(0xffffffffu, alive ? key : 0xFFFFFFFFu);
-        if (md == 0xFFFFFFFFu) break;
-        const uint32_t mi = __reduce_min_sync(0xffffffffu, (alive && key == md) ? (uint32_t)idx : 0xFFFFFFFFu);
-        if (alive && key == md && (uint32_t)idx == mi) { rank = m; alive = false; }
-      }
-      if (rank >= 0) {
+      if (key != 0xFFFFFFFFu && rank < cnt_out) {
         float gx, gy;
         fr.world(idx, gx, gy);
         const size_t o = ((size_t)b * T1 + t) * M + rank;

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(128, NB_SMMA_BLOCKS) dune_screen_mma_kernel(co
     }
     if (n <= kCandMax && !prm.calibrate) {  // nothing to screen: every point is a candidate
       if (tid < n) { out_idx[tid] = tid; out_dt[tid] = __int_as_float(0x7fc00000); }
-      if (tid == 0) prm.cand_cnt[item] = n;
+      if (tid == 0) { prm.cand_cnt[item] = n; tc::refine_append(prm, item, n); }
       continue;
     }
     if (staged != item) {
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(128, NB_SMMA_BLOCKS) dune_screen_mma_kernel(co
     }
     if (n <= kCandMax) {  // calibration mode: all points (they belong to warp 0's only tile), with their screened distance
       if (k0 != 0xFFFFFFFFu) { out_idx[k0 & 0x1FFu] = (int)(k0 & 0x1FFu); out_dt[k0 & 0x1FFu] = d0; }
-      if (tid == 0) prm.cand_cnt[item] = n;
+      if (tid == 0) { prm.cand_cnt[item] = n; tc::refine_append(prm, item, n); }
       continue;
     }
     // ---- tau = the M-th smallest upper bound: unique 32-bit keys, M REDUX rounds per warp (each removes the one entry that equals
@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(128, NB_SMMA_BLOCKS) dune_screen_mma_kernel(co
       if (tid < nc) { out_idx[tid] = list_s[tid]; out_dt[tid] = ldt_s[tid]; }
       if (tid == 0) {
         prm.cand_cnt[item] = nc;
+        tc::refine_append(prm, item, nc);
         atomicAdd(&prm.screen_stats[2], (unsigned)nc);
         atomicAdd(&prm.screen_stats[3], 1u);
       }

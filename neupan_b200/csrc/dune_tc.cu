@@ -121,7 +121,7 @@ int launch_dune_tc(const DuneParams& prm_in, const unsigned char* d_image, const
   if (variant == 4) {
     // screening: (1) interval pass over all points, (2) exact evaluation of the candidates, (3) the exact kernel for the items the
     // screen could not narrow down to 32 candidates (below, with only_flagged)
-    if (!d_screen_image || !prm.cand_idx || !prm.cand_cnt || !prm.cand_dt || !prm.screen_stats || !prm.flag_list || !prm.flag_count) {
+    if (!d_screen_image || !prm.cand_idx || !prm.cand_cnt || !prm.cand_dt || !prm.screen_stats || !prm.flag_list || !prm.flag_count || !prm.refine_list) {
       snprintf(err, errlen, "screening buffers are not allocated");
       return -1;
     }
@@ -138,7 +138,7 @@ int launch_dune_tc(const DuneParams& prm_in, const unsigned char* d_image, const
     int per_s = (int)(233472 / (smem_s + 2048));
     per_s = per_s > 4 ? 4 : (per_s < 1 ? 1 : per_s);
     const int screen_mma = prm.screen_mma;
-    cudaError_t e = cudaMemsetAsync(prm.flag_count, 0, sizeof(int32_t), st);
+    cudaError_t e = cudaMemsetAsync(prm.flag_count, 0, 3 * sizeof(int32_t), st);
     const size_t smem_m = dune_screen_mma_smem_bytes(prm.N, prm.M);
     if (screen_mma && prm.N <= 512 && (long long)smem_m <= max_smem_optin) {  // larger clouds: the tcgen05 screen kernel (key arrays in shared memory)
       // no TMEM in this kernel: residency is whatever registers and shared memory admit
@@ -169,7 +169,7 @@ int launch_dune_tc(const DuneParams& prm_in, const unsigned char* d_image, const
     if (e == cudaSuccess) e = fast_r ? cudaFuncSetAttribute(dune_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)
                                       : cudaFuncSetAttribute(dune_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
     if (e == cudaSuccess) {
-      int grid = sm_count * 4;
+      int grid = sm_count * 4;  // the number of work units is only known on the device: a persistent grid sized for the worst case
       const int groups = (items_ + 7) / 8;
       if (grid > groups) grid = groups;
       if (fast_r) dune_refine_kernel<true><<<grid, 128, smem_r, st>>>(prm, d_image);

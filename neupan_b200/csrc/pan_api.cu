@@ -89,7 +89,7 @@ struct nb_pan {
   unsigned char* d_tc_image = nullptr;  // UMMA operand image of the tcgen05 DUNE kernel
   int tc_flags = 0;                     // build_tc_image(): bit 0 = bounded tanh arguments
   unsigned char* d_tc_screen = nullptr; // operand image of the screening network (NB_OPT_DUNE_KERNEL = 4)
-  int32_t *cand_idx = nullptr, *cand_cnt = nullptr, *flag_list = nullptr, *flag_count = nullptr;
+  int32_t *cand_idx = nullptr, *cand_cnt = nullptr, *flag_list = nullptr, *flag_count = nullptr, *refine_list = nullptr;
   float* cand_dt = nullptr;
   unsigned* screen_stats = nullptr;
   float c_mu = 0.012f;                  // bound on the screening network's |mu~ - mu|: set by calibrate_screen() to 4 x the largest error
@@ -285,7 +285,7 @@ int calibrate_screen(nb_pan* p, cudaStream_t st) {
     prm.sel_mu = p->sel_mu; prm.sel_lam = p->sel_lam; prm.sel_pts = p->sel_pts; prm.sel_dist = p->sel_dist; prm.sel_count = p->sel_count; prm.min_dist = d_md;
     prm.B = Bc; prm.N = N; prm.T = c.receding; prm.M = c.nrmp_max_num; prm.dt = (float)c.step_time; prm.geo = p->geo;
     prm.cand_idx = p->cand_idx; prm.cand_cnt = p->cand_cnt; prm.cand_dt = p->cand_dt; prm.screen_stats = p->screen_stats; prm.c_mu = p->c_mu;
-    prm.flag_list = p->flag_list; prm.flag_count = p->flag_count; prm.calibrate = 1;
+    prm.flag_list = p->flag_list; prm.flag_count = p->flag_count; prm.refine_list = p->refine_list; prm.calibrate = 1;
     for (int shape = 0; shape < 2 && rc == NB_OK; ++shape) {  // both screening kernels (tcgen05 / mma.sync): the bound holds whichever option is set later
       prm.screen_mma = shape;
       rc = launch_dune(p, prm, st);
@@ -390,7 +390,8 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
     NB_CUDA(dalloc(&p->cand_dt, (size_t)cfg->max_envs * (cfg->receding + 1) * nb::kCandMax));
     NB_CUDA(dalloc(&p->cand_cnt, (size_t)cfg->max_envs * (cfg->receding + 1)));
     NB_CUDA(dalloc(&p->flag_list, (size_t)cfg->max_envs * (cfg->receding + 1)));
-    NB_CUDA(dalloc(&p->flag_count, (size_t)8));  // one counter per internal stream
+    NB_CUDA(dalloc(&p->flag_count, (size_t)32));  // 4 words per internal stream: flagged items, the two refine list lengths
+    NB_CUDA(dalloc(&p->refine_list, (size_t)2 * cfg->max_envs * (cfg->receding + 1)));
     NB_CUDA(dalloc(&p->screen_stats, (size_t)4));
     NB_CUDA(cudaMemset(p->screen_stats, 0, 4 * sizeof(unsigned)));
     if (const char* e = getenv("NB_SCREEN_CMU")) p->c_mu = (float)atof(e);
@@ -439,7 +440,7 @@ int nb_pan_destroy(nb_pan_t* p) {
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   void* bufs[] = {p->d_tc_image, p->d_image, p->d_weights, p->sel_mu, p->sel_lam, p->sel_pts, p->sel_dist, p->sel_count, p->prev_s, p->prev_u, p->prev_mu,
                   p->prev_lam, p->prev_count, p->prev_valid, p->active, p->iters, p->status, p->ipm_it, p->min_dist, p->h_in, p->h_out, p->h_np, p->h_io,
-                  p->d_tc_screen, p->cand_idx, p->cand_cnt, p->cand_dt, p->screen_stats, p->flag_list, p->flag_count, p->warm, p->warm_valid, p->work_counters, p->adj_rec, p->adj_gs, p->adj_gu, p->adj_gd, p->adj_gtheta, p->adj_valid};
+                  p->d_tc_screen, p->cand_idx, p->cand_cnt, p->cand_dt, p->screen_stats, p->flag_list, p->flag_count, p->refine_list, p->warm, p->warm_valid, p->work_counters, p->adj_rec, p->adj_gs, p->adj_gu, p->adj_gd, p->adj_gtheta, p->adj_valid};
   for (void* b : bufs)
     if (b) cudaFree(b);
   delete p;
@@ -528,7 +529,7 @@ int nb_dune_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const
   prm.min_dist = out_min_distance;
   prm.B = B; prm.N = N; prm.T = p->cfg.receding; prm.M = p->cfg.nrmp_max_num; prm.dt = (float)p->cfg.step_time; prm.geo = p->geo;
   prm.cand_idx = p->cand_idx; prm.cand_cnt = p->cand_cnt; prm.cand_dt = p->cand_dt; prm.screen_stats = p->screen_stats; prm.c_mu = p->c_mu;
-  prm.flag_list = p->flag_list; prm.flag_count = p->flag_count; prm.screen_mma = p->screen_mma;
+  prm.flag_list = p->flag_list; prm.flag_count = p->flag_count; prm.refine_list = p->refine_list; prm.screen_mma = p->screen_mma;
   return launch_dune(p, prm, (cudaStream_t)stream);
 }
 
@@ -595,7 +596,7 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
         d.B = nb_; d.N = N; d.T = T; d.M = c.nrmp_max_num; d.dt = (float)c.step_time; d.geo = p->geo;
         d.cand_idx = p->cand_idx + (size_t)lo * T1s * nb::kCandMax; d.cand_dt = p->cand_dt + (size_t)lo * T1s * nb::kCandMax;
         d.cand_cnt = p->cand_cnt + (size_t)lo * T1s; d.screen_stats = p->screen_stats; d.c_mu = p->c_mu;
-        d.flag_list = p->flag_list + (size_t)lo * T1s; d.flag_count = p->flag_count + counter_slot;
+        d.flag_list = p->flag_list + (size_t)lo * T1s; d.flag_count = p->flag_count + 4 * counter_slot; d.refine_list = p->refine_list + (size_t)2 * lo * T1s;
         d.screen_mma = p->screen_mma;
         d.skip_t0 = (k > 0 && p->dune_skip_t0) ? 1 : 0;  // the step-0 items of iteration 0 stand (DuneParams::skip_t0)
         if (int rc = launch_dune(p, d, s, dune_cta_limit)) return rc;
