@@ -56,6 +56,7 @@ struct NrmpParams {
   float* warm; int32_t* warm_valid;
   int warm_check_it; double warm_check_gap;  // a warm start whose gap is still above warm_check_gap at iteration warm_check_it restarts cold
   int* work_counter;  // dynamic env -> warp assignment (see nrmp_kernel), or nullptr
+  int defer_stop;     // 1 = the solve kernel leaves the stop criterion / PAN.current_nom_values update (section 8) to nrmp_stop_kernel
   // differentiable mode (LON): per-env record of this solve for nrmp_adjoint_kernel, nrmp_adj_doubles(T, M)
   // doubles each, and a validity flag; nullptr = inference
   double* adj_save; int32_t* adj_valid;
@@ -154,6 +155,67 @@ __device__ __forceinline__ float rcpf(double x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)x));
   return r;
+}
+
+// ---- stop criterion of one environment (pan.py:215-243) and the update of PAN.current_nom_values: one warp.  Called at the end of the
+// solve, or -- NrmpParams::defer_stop -- from nrmp_stop_kernel: the ~1300 floats it reads per environment are latency the solve
+// kernel cannot hide (6.8 % of its warp time on C4), a bandwidth kernel over the batch reads them in a few microseconds.
+template <int TT, int MM>
+__device__ __forceinline__ void nrmp_stop_env(const NrmpParams& prm, const int b, const int lane) {
+  const int T = TT > 0 ? TT : prm.T, M = TT > 0 ? MM : prm.M, T1 = T + 1;
+  const float* os = prm.out_s + (size_t)b * 3 * T1;
+  const float* ou = prm.out_u + (size_t)b * 2 * T;
+  if (prm.prev_valid) {
+    const int E = prm.E;
+    const int cur_cnt = (prm.fa || M == 0 || !prm.sel_count) ? 0 : prm.sel_count[b];
+    const int valid = prm.prev_valid[b];
+    const int pcnt = prm.prev_count[b];
+    float* ps = prm.prev_s + (size_t)b * 3 * T1;
+    float* pu_ = prm.prev_u + (size_t)b * 2 * T;
+    float* pmu = prm.prev_mu ? prm.prev_mu + (size_t)b * T1 * M * E : nullptr;
+    float* plam = prm.prev_lam ? prm.prev_lam + (size_t)b * T1 * M * 2 : nullptr;
+    const float* cmu = prm.sel_mu ? prm.sel_mu + (size_t)b * T1 * M * E : nullptr;
+    const float* clam = prm.sel_lam ? prm.sel_lam + (size_t)b * T1 * M * 2 : nullptr;
+    float diff = 0.f;
+    if (valid) {
+      if (cur_cnt == 0 || pcnt == 0) {
+        double a1 = 0, a2 = 0;
+        NB_LL(i, 3 * T1) { const double d = (double)os[i] - (double)ps[i]; a1 += d * d; }
+        NB_LL(i, 2 * T) { const double d = (double)ou[i] - (double)pu_[i]; a2 += d * d; }
+        const float n1f = sqrtf((float)warp_sum(a1)), n2f = sqrtf((float)warp_sum(a2));
+        diff = n1f * n1f + n2f * n2f;
+      } else {
+        const int en = cur_cnt < pcnt ? cur_cnt : pcnt;
+        double a1 = 0, a2 = 0;
+        NB_LL(i, T1 * en * E) {
+          const int tt = i / (en * E), rem = i - tt * en * E;  // rem = col*E + e, col < en
+          const size_t o = (size_t)tt * M * E + rem;
+          const double d = (double)cmu[o] - (double)pmu[o];
+          a1 += d * d;
+        }
+        NB_LL(i, T1 * en * 2) {
+          const int tt = i / (en * 2), rem = i - tt * en * 2;
+          const size_t o = (size_t)tt * M * 2 + rem;
+          const double d = (double)clam[o] - (double)plam[o];
+          a2 += d * d;
+        }
+        const float md = sqrtf((float)warp_sum(a1)) / (float)en, ld = sqrtf((float)warp_sum(a2)) / (float)en;
+        diff = md * md + ld * ld;
+      }
+    }
+    __syncwarp();
+    NB_LL(i, 3 * T1) ps[i] = os[i];
+    NB_LL(i, 2 * T) pu_[i] = ou[i];
+    if (pmu && cmu) {
+      NB_LL(i, T1 * M * E) pmu[i] = cmu[i];
+      NB_LL(i, T1 * M * 2) plam[i] = clam[i];
+    }
+    if (lane == 0) {
+      prm.prev_valid[b] = 1;
+      prm.prev_count[b] = cur_cnt;
+      if (valid && diff < prm.iter_threshold && prm.active) prm.active[b] = 0;
+    }
+  }
 }
 
 // SMALL: 2T <= 32, every lane owns at most one row of the reduced system (one register slot in the
@@ -994,57 +1056,7 @@ __device__ __forceinline__ void nrmp_solve_env(const NrmpParams& prm, const int 
   __syncwarp();
 
   // ---- 8. stop criterion (pan.py:215-243) ----------------------------------------------------------
-  if (prm.prev_valid) {
-    const int E = prm.E;
-    const int cur_cnt = (prm.fa || M == 0 || !prm.sel_count) ? 0 : prm.sel_count[b];
-    const int valid = prm.prev_valid[b];
-    const int pcnt = prm.prev_count[b];
-    float* ps = prm.prev_s + (size_t)b * 3 * T1;
-    float* pu_ = prm.prev_u + (size_t)b * 2 * T;
-    float* pmu = prm.prev_mu ? prm.prev_mu + (size_t)b * T1 * M * E : nullptr;
-    float* plam = prm.prev_lam ? prm.prev_lam + (size_t)b * T1 * M * 2 : nullptr;
-    const float* cmu = prm.sel_mu ? prm.sel_mu + (size_t)b * T1 * M * E : nullptr;
-    const float* clam = prm.sel_lam ? prm.sel_lam + (size_t)b * T1 * M * 2 : nullptr;
-    float diff = 0.f;
-    if (valid) {
-      if (cur_cnt == 0 || pcnt == 0) {
-        double a1 = 0, a2 = 0;
-        NB_LL(i, 3 * T1) { const double d = (double)os[i] - (double)ps[i]; a1 += d * d; }
-        NB_LL(i, 2 * T) { const double d = (double)ou[i] - (double)pu_[i]; a2 += d * d; }
-        const float n1f = sqrtf((float)warp_sum(a1)), n2f = sqrtf((float)warp_sum(a2));
-        diff = n1f * n1f + n2f * n2f;
-      } else {
-        const int en = cur_cnt < pcnt ? cur_cnt : pcnt;
-        double a1 = 0, a2 = 0;
-        NB_LL(i, T1 * en * E) {
-          const int tt = i / (en * E), rem = i - tt * en * E;  // rem = col*E + e, col < en
-          const size_t o = (size_t)tt * M * E + rem;
-          const double d = (double)cmu[o] - (double)pmu[o];
-          a1 += d * d;
-        }
-        NB_LL(i, T1 * en * 2) {
-          const int tt = i / (en * 2), rem = i - tt * en * 2;
-          const size_t o = (size_t)tt * M * 2 + rem;
-          const double d = (double)clam[o] - (double)plam[o];
-          a2 += d * d;
-        }
-        const float md = sqrtf((float)warp_sum(a1)) / (float)en, ld = sqrtf((float)warp_sum(a2)) / (float)en;
-        diff = md * md + ld * ld;
-      }
-    }
-    __syncwarp();
-    NB_LL(i, 3 * T1) ps[i] = os[i];
-    NB_LL(i, 2 * T) pu_[i] = ou[i];
-    if (pmu && cmu) {
-      NB_LL(i, T1 * M * E) pmu[i] = cmu[i];
-      NB_LL(i, T1 * M * 2) plam[i] = clam[i];
-    }
-    if (lane == 0) {
-      prm.prev_valid[b] = 1;
-      prm.prev_count[b] = cur_cnt;
-      if (valid && diff < prm.iter_threshold && prm.active) prm.active[b] = 0;
-    }
-  }
+  if (!prm.defer_stop) nrmp_stop_env<TT, MM>(prm, b, lane);
 }
 
 // ---- adjoint of one NRMP solve (differentiable mode; replaces the backward pass of CvxpyLayer, nrmp.py:144) -----------------
@@ -1215,6 +1227,14 @@ __global__ void __launch_bounds__((TT == 10 && MM == 10) ? 32 * NB_NRMP_WPC : 64
     nrmp_solve_env<HPL, SMALL, TT, MM>(prm, b, wsp, ptab, lane);
     __syncwarp();
   }
+}
+
+// the deferred section 8: one warp per environment, the same arithmetic in the same order as inside the solve
+__global__ void __launch_bounds__(128) nrmp_stop_kernel(const NrmpParams prm) {
+  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= prm.B) return;
+  if (prm.active && prm.active[b] == 0) return;
+  nrmp_stop_env<0, 0>(prm, b, lane);
 }
 
 #undef NB_LL

@@ -112,6 +112,7 @@ struct nb_pan {
   int* work_counters = nullptr;     // dynamic env -> warp assignment of the NRMP kernel, one counter per internal stream
   int dune_skip_t0 = 1;             // NB_OPT_DUNE_SKIP_T0: PAN iterations k > 0 keep the step-0 items of iteration 0 (screening variant)
   int screen_mma = 1;               // NB_OPT_DUNE_SCREEN_MMA: screening pass on mma.sync (N <= 512) instead of tcgen05
+  int nrmp_defer_stop_min = 256;    // NB_NRMP_DEFER_STOP_MIN (developer switch, read at create): smallest batch whose stop criterion runs as its own kernel
   int nrmp_dynamic = 1;             // NB_NRMP_STATIC=1 (developer switch, read at create) turns the persistent-warp schedule off
   float* warm = nullptr;            // NRMP warm-start records, nrmp_warm_floats(T, M) per environment
   int32_t* warm_valid = nullptr;
@@ -206,6 +207,9 @@ int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st, int counter_slot
     prm.acce[i] = c.max_acce[i] * c.step_time;
   }
   for (int e = 0; e < nb::kMaxEdges; ++e) prm.h[e] = p->geo.h[e];
+  // large batches: the stop criterion's ~1300 dependent global reads per environment leave the solve kernel (where each warp waits for
+  // them alone) for a kernel of its own; small batches keep it inside (one launch less per PAN iteration matters more there)
+  prm.defer_stop = (prm.prev_valid != nullptr && prm.B >= p->nrmp_defer_stop_min) ? 1 : 0;
   const size_t wd = nb::nrmp_warp_doubles(prm.T, prm.M);
   const size_t extra = nb::nrmp_cta_extra_bytes(prm.T);
   const int TM = prm.T * prm.M;
@@ -232,6 +236,10 @@ int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st, int counter_slot
     }
     kern<<<grid, warps * 32, smem, st>>>(prm, warps, (int)wd);
     ++g_launches;
+    if (prm.defer_stop) {  // section 8 (stop criterion, PAN.current_nom_values) as a bandwidth kernel over the batch
+      nb::nrmp_stop_kernel<<<(prm.B + 3) / 4, 128, 0, st>>>(prm);
+      ++g_launches;
+    }
     NB_CUDA(cudaGetLastError());
     return NB_OK;
   };
@@ -417,6 +425,7 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
   NB_CUDA(dalloc(&p->warm_valid, B));
   NB_CUDA(dalloc(&p->work_counters, (size_t)8));
   if (getenv("NB_NRMP_STATIC")) p->nrmp_dynamic = 0;
+  if (const char* e = getenv("NB_NRMP_DEFER_STOP_MIN")) p->nrmp_defer_stop_min = atoi(e);
   if (const char* e = getenv("NB_DUNE_SKIP_T0")) p->dune_skip_t0 = atoi(e) != 0;  // developer overrides of the option defaults
   if (const char* e = getenv("NB_SCREEN_MMA")) p->screen_mma = atoi(e) != 0;
   if (const char* e = getenv("NB_NRMP_RESTART_IT")) p->warm_check_it = atoi(e);

@@ -177,6 +177,32 @@ def test_stop_criterion_and_state_across_calls():
     assert pan.iterations.cpu().numpy().min() >= 2  # first call after a reset never stops at iteration 1
 
 
+def test_stop_criterion_as_its_own_kernel_equals_the_fused_one():
+    """Batches of >= 256 environments run section 8 of the NRMP kernel (stop criterion, PAN.current_nom_values) as nrmp_stop_kernel
+    after the solve; smaller ones keep it inside.  Same arithmetic, same order: trajectories, iteration counts and the state carried
+    into the next call are equal bit for bit (NB_NRMP_DEFER_STOP_MIN is read when the handle is created)."""
+    import os
+
+    cfg = CONFIGS["C5"]
+    inp = make_inputs(cfg, B=300, scene="obstacles")
+    outs = []
+    for thr_min in ("1000000", "1"):
+        os.environ["NB_NRMP_DEFER_STOP_MIN"] = thr_min
+        try:
+            pan = make_pan(cfg, K=6, iter_threshold=0.1, max_envs=300)
+            a = run_pan(pan, inp)
+            it1 = pan.iterations.cpu().numpy().copy()
+            b = run_pan(pan, inp)  # second call: starts from the state the first one left
+            outs.append((a, it1, b, pan.iterations.cpu().numpy().copy()))
+        finally:
+            del os.environ["NB_NRMP_DEFER_STOP_MIN"]
+    (a0, i0, b0, j0), (a1, i1, b1, j1) = outs
+    for x, y in zip(a0 + b0, a1 + b1):
+        assert np.array_equal(x, y)
+    assert np.array_equal(i0, i1) and np.array_equal(j0, j1)
+    assert i0.min() < 6  # the criterion did fire
+
+
 def test_nrmp_warm_start_reaches_the_cold_start_optimum():
     """NB_OPT_NRMP_WARM: iteration 2's solve starts from iteration 1's solution; same optimum to the solver tolerance, fewer
     interior point iterations.  (K = 2: the first solve is cold in both runs, so the inputs of the second are bit-identical.)"""
