@@ -455,7 +455,7 @@ def run_ours(args):
                                 parallelism=f"env-sharded x{world}, one all_gather of {per_env} floats/env per step (inside the timed region, device-resident and e2e)",
                                 l2="2 rotating input sets + 256 MiB flush between timed steps", scene="annulus (SURVEY 8d)"),
                     e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             ms_per_step=e2e_ms, api="neupan_b200.parallel.ShardedPAN.step on pinned host tensors: H2D -> PAN.forward (nb_pan_forward) -> all_gather -> D2H of the gathered trajectories"),
+                             ms_per_step=e2e_ms, api="neupan_b200.parallel.ShardedPAN.step on pinned host tensors: nb_pan_forward_h2d (upload in env chunks on a copy stream, the first DUNE pass of a chunk starts when its points have landed) -> all_gather -> D2H of the gathered trajectories"),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu, envs_with_solver_status=status_bad,
                     pan_iterations_mean=iters_mean, control_steps_per_s=world / (ms * 1e-3), **extra)
         print(json.dumps(line))

@@ -106,6 +106,16 @@ int nb_pan_forward_host(nb_pan_t* pan, int32_t B, int32_t N,
                         float* out_s, float* out_u, float* out_d, float* out_min_distance,
                         int32_t* out_iters, int32_t* out_status, void* stream);
 
+/* HOST inputs (pinned memory for a real overlap), DEVICE outputs, asynchronous on `stream` like nb_pan_forward: the inputs are uploaded
+ * on an internal copy stream in environment chunks and the first DUNE pass of a chunk starts as soon as its points have landed, so
+ * the upload of the cloud hides behind the first PAN iteration (the callers that keep results on the device -- e.g. to exchange them
+ * between GPUs before they travel back -- use this one; nb_pan_forward_host is this call plus the download and a synchronise). */
+int nb_pan_forward_h2d(nb_pan_t* pan, int32_t B, int32_t N,
+                        const float* nom_s, const float* nom_u, const float* ref_s, const float* ref_us,
+                        const float* points, const float* velocities, const int32_t* num_points,
+                        float* out_s, float* out_u, float* out_d, float* out_min_distance,
+                        int32_t* out_iters, int32_t* out_status, void* stream);
+
 /* Replaces NRMP.update_adjust_parameters_value (nrmp.py:171-217). */
 int nb_pan_set_adjust(nb_pan_t* pan, const float q_s[3], float p_u, float eta, float d_max, float d_min);
 /* iter_num / iter_threshold are plain attributes in the reference (pan.py:63-64). */

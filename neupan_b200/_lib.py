@@ -64,6 +64,7 @@ SYMBOLS = {
     "nb_pan_destroy": (C.c_int, [C.c_void_p]),
     "nb_pan_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [_FP] * 13 + [C.c_void_p]),
     "nb_pan_forward_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [_FP] * 13 + [C.c_void_p]),
+    "nb_pan_forward_h2d": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [_FP] * 13 + [C.c_void_p]),
     "nb_pan_set_adjust": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 3), C.c_float, C.c_float, C.c_float, C.c_float]),
     "nb_pan_set_iteration": (C.c_int, [C.c_void_p, C.c_int32, C.c_float]),
     "nb_pan_set_option": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),

@@ -205,10 +205,12 @@ class PAN(torch.nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, nom_s: torch.Tensor, nom_u: torch.Tensor, ref_s: torch.Tensor, ref_us: torch.Tensor,
-                obs_points: torch.Tensor = None, point_velocities: torch.Tensor = None, num_points: torch.Tensor = None):
+                obs_points: torch.Tensor = None, point_velocities: torch.Tensor = None, num_points: torch.Tensor = None, device_out: bool = False):
         """pan.py:109-147.  Shapes (3,T+1),(2,T),(3,T+1),(T,),(2,N),(2,N) or the same with a leading
         B.  ``num_points`` (B,) int32 marks ragged batches (extension).  Returns tensors on the
-        device of ``nom_s`` with the same batching."""
+        device of ``nom_s`` with the same batching.  ``device_out=True`` with CPU (ideally pinned) inputs: the results stay on the GPU
+        and the call is asynchronous (``nb_pan_forward_h2d``: chunked upload overlapped with the first DUNE pass) -- what a
+        caller wants that exchanges results between GPUs before they travel back (``parallel.ShardedPAN``)."""
         batched = nom_s.dim() == 3
         un = (lambda t: t) if batched else (lambda t: None if t is None else t.unsqueeze(0))
         nom_s, nom_u, ref_s, ref_us = un(nom_s), un(nom_u), un(ref_s), un(ref_us)
@@ -243,13 +245,15 @@ class PAN(torch.nn.Module):
         lib = self._ensure_handle(B, N)
         self._push_settings(lib)
 
-        host = nom_s.device.type != "cuda"
+        host_in = nom_s.device.type != "cuda"
+        host = host_in and not device_out  # results on the host (synchronous call)
+        in_dev = torch.device("cpu") if host_in else self.device
         io_dev = torch.device("cpu") if host else self.device
-        prep = lambda t: None if t is None else t.detach().to(device=io_dev, dtype=torch.float32).contiguous()
+        prep = lambda t: None if t is None else t.detach().to(device=in_dev, dtype=torch.float32).contiguous()
         nom_s, nom_u, ref_s, ref_us = prep(nom_s), prep(nom_u), prep(ref_s), prep(ref_us)
         obs_points, point_velocities = prep(obs_points), prep(point_velocities)
         if num_points is not None:
-            num_points = num_points.detach().to(device=io_dev, dtype=torch.int32).contiguous()
+            num_points = num_points.detach().to(device=in_dev, dtype=torch.int32).contiguous()
         mk = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype, device=io_dev, pin_memory=host and torch.cuda.is_available())
         out_md, out_it, out_st = mk(B), mk(B, dtype=torch.int32), mk(B, dtype=torch.int32)
         # differentiable mode (LON): any adjust parameter that requires grad while autograd is recording
@@ -264,7 +268,7 @@ class PAN(torch.nn.Module):
             out_s, out_u, out_d = mk(B, 3, T + 1), mk(B, 2, T), mk(B, T)
             with torch.cuda.device(self.device):
                 stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-                fn = lib.nb_pan_forward_host if host else lib.nb_pan_forward
+                fn = lib.nb_pan_forward_host if host else (lib.nb_pan_forward_h2d if host_in else lib.nb_pan_forward)
                 _lib.check(fn(self._handle, B, N, _ptr(nom_s), _ptr(nom_u), _ptr(ref_s), _ptr(ref_us), _ptr(obs_points), _ptr(point_velocities),
                               _ptr(num_points), _ptr(out_s), _ptr(out_u), _ptr(out_d), _ptr(out_md), _ptr(out_it), _ptr(out_st), stream))
             return out_s, out_u, out_d

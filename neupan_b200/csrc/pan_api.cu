@@ -100,6 +100,11 @@ struct nb_pan {
   int overlap = 1;                   // NB_OPT_OVERLAP: number of env sub-batches pipelined on internal streams
   cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  // host-input entry points: uploads run on copy_stream in env chunks; ev_chunk[c] = chunk c (and everything before it) has landed
+  static constexpr int kMaxChunks = 8;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_chunk[kMaxChunks] = {}, ev_inputs_free = nullptr;
+  int h2d_chunks = 4;               // NB_H2D_CHUNKS (developer switch, read at create); 1 = no overlap
   float *sel_mu = nullptr, *sel_lam = nullptr, *sel_pts = nullptr, *sel_dist = nullptr;
   int32_t* sel_count = nullptr;
   float *prev_s = nullptr, *prev_u = nullptr, *prev_mu = nullptr, *prev_lam = nullptr;
@@ -426,6 +431,7 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
   NB_CUDA(dalloc(&p->work_counters, (size_t)8));
   if (getenv("NB_NRMP_STATIC")) p->nrmp_dynamic = 0;
   if (const char* e = getenv("NB_NRMP_DEFER_STOP_MIN")) p->nrmp_defer_stop_min = atoi(e);
+  if (const char* e = getenv("NB_H2D_CHUNKS")) { p->h2d_chunks = atoi(e); if (p->h2d_chunks < 1) p->h2d_chunks = 1; if (p->h2d_chunks > nb_pan::kMaxChunks) p->h2d_chunks = nb_pan::kMaxChunks; }
   if (const char* e = getenv("NB_DUNE_SKIP_T0")) p->dune_skip_t0 = atoi(e) != 0;  // developer overrides of the option defaults
   if (const char* e = getenv("NB_SCREEN_MMA")) p->screen_mma = atoi(e) != 0;
   if (const char* e = getenv("NB_NRMP_RESTART_IT")) p->warm_check_it = atoi(e);
@@ -447,6 +453,10 @@ int nb_pan_destroy(nb_pan_t* p) {
     if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
   }
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+  if (p->ev_inputs_free) cudaEventDestroy(p->ev_inputs_free);
+  for (cudaEvent_t e : p->ev_chunk)
+    if (e) cudaEventDestroy(e);
   void* bufs[] = {p->d_tc_image, p->d_image, p->d_weights, p->sel_mu, p->sel_lam, p->sel_pts, p->sel_dist, p->sel_count, p->prev_s, p->prev_u, p->prev_mu,
                   p->prev_lam, p->prev_count, p->prev_valid, p->active, p->iters, p->status, p->ipm_it, p->min_dist, p->h_in, p->h_out, p->h_np, p->h_io,
                   p->d_tc_screen, p->cand_idx, p->cand_cnt, p->cand_dt, p->screen_stats, p->flag_list, p->flag_count, p->refine_list, p->warm, p->warm_valid, p->work_counters, p->adj_rec, p->adj_gs, p->adj_gu, p->adj_gd, p->adj_gtheta, p->adj_valid};
@@ -555,9 +565,29 @@ int nb_nrmp_forward(nb_pan_t* p, int32_t B, const float* nom_s, const float* nom
   return launch_nrmp(p, prm, (cudaStream_t)stream);
 }
 
+namespace {
+// env chunks whose inputs arrive on another stream: chunk c = environments [bound[c], bound[c+1]), usable once ev[c] has fired
+struct ChunkPlan {
+  int n = 0;
+  int bound[nb_pan::kMaxChunks + 1] = {};
+  cudaEvent_t ev[nb_pan::kMaxChunks] = {};
+};
+int pan_forward_impl(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const float* nom_u, const float* ref_s, const float* ref_us,
+                     const float* points, const float* velocities, const int32_t* num_points, float* out_s, float* out_u, float* out_d,
+                     float* out_min_distance, int32_t* out_iters, int32_t* out_status, void* stream, const ChunkPlan* plan);
+}  // namespace
+
 int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const float* nom_u, const float* ref_s, const float* ref_us,
                    const float* points, const float* velocities, const int32_t* num_points, float* out_s, float* out_u, float* out_d,
                    float* out_min_distance, int32_t* out_iters, int32_t* out_status, void* stream) {
+  return pan_forward_impl(p, B, N, nom_s, nom_u, ref_s, ref_us, points, velocities, num_points, out_s, out_u, out_d, out_min_distance, out_iters,
+                          out_status, stream, nullptr);
+}
+
+namespace {
+int pan_forward_impl(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const float* nom_u, const float* ref_s, const float* ref_us,
+                     const float* points, const float* velocities, const int32_t* num_points, float* out_s, float* out_u, float* out_d,
+                     float* out_min_distance, int32_t* out_iters, int32_t* out_status, void* stream, const ChunkPlan* plan) {
   if (int rc = check_forward_args(p, B, N)) return rc;
   if (!nom_s || !nom_u || !ref_s || !ref_us || !out_s || !out_u || !out_d) return fail(NB_ERR_INVALID, "null tensor argument");
   if (velocities && !points) return fail(NB_ERR_INVALID, "velocities given without points");
@@ -581,6 +611,7 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
     p->adj_iters = (int)Ks;
   }
   if (p->differentiable) NB_CUDA(cudaMemsetAsync(p->adj_valid, 0, (size_t)p->adj_iters * c.max_envs * sizeof(int32_t), st));
+  if (plan && plan->n > 0) NB_CUDA(cudaStreamWaitEvent(st, plan->ev[0], 0));  // the small tensors travel ahead of chunk 0
   const int tb = 128, gb = (B + tb - 1) / tb;
   init_run_kernel<<<gb, tb, 0, st>>>(B, p->active, p->iters, p->status, p->min_dist, p->sel_count, p->warm_valid);
   ++g_launches;
@@ -608,7 +639,31 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
         d.flag_list = p->flag_list + (size_t)lo * T1s; d.flag_count = p->flag_count + 4 * counter_slot; d.refine_list = p->refine_list + (size_t)2 * lo * T1s;
         d.screen_mma = p->screen_mma;
         d.skip_t0 = (k > 0 && p->dune_skip_t0) ? 1 : 0;  // the step-0 items of iteration 0 stand (DuneParams::skip_t0)
-        if (int rc = launch_dune(p, d, s, dune_cta_limit)) return rc;
+        if (k == 0 && plan && plan->n > 1 && lo == 0 && hi == B) {
+          // the first DUNE pass chunk by chunk, each as soon as its points have landed: the upload of chunk c+1 overlaps the work on chunk c
+          for (int ch = 0; ch < plan->n; ++ch) {
+            const int clo = plan->bound[ch], chi = plan->bound[ch + 1];
+            if (chi <= clo) continue;
+            NB_CUDA(cudaStreamWaitEvent(s, plan->ev[ch], 0));
+            nb::DuneParams dc = d;
+            dc.nom_s = d.nom_s + (size_t)clo * 3 * T1s; dc.points = d.points + (size_t)clo * 2 * N;
+            dc.velocities = d.velocities ? d.velocities + (size_t)clo * 2 * N : nullptr;
+            dc.num_points = d.num_points ? d.num_points + clo : nullptr;
+            dc.active = d.active + clo;
+            dc.sel_mu = d.sel_mu + (size_t)clo * T1s * Ms * Es; dc.sel_lam = d.sel_lam + (size_t)clo * T1s * Ms * 2;
+            dc.sel_pts = d.sel_pts + (size_t)clo * T1s * Ms * 2; dc.sel_dist = d.sel_dist + (size_t)clo * T1s * Ms; dc.sel_count = d.sel_count + clo;
+            dc.min_dist = d.min_dist + clo;
+            dc.B = chi - clo;
+            dc.cand_idx = d.cand_idx + (size_t)clo * T1s * nb::kCandMax; dc.cand_dt = d.cand_dt + (size_t)clo * T1s * nb::kCandMax;
+            dc.cand_cnt = d.cand_cnt + (size_t)clo * T1s;
+            dc.flag_list = d.flag_list + (size_t)clo * T1s; dc.refine_list = d.refine_list + (size_t)2 * clo * T1s;
+            if (int rc = launch_dune(p, dc, s, dune_cta_limit)) return rc;
+          }
+        } else {
+          if (k == 0 && plan)
+            for (int ch = 1; ch < plan->n; ++ch) NB_CUDA(cudaStreamWaitEvent(s, plan->ev[ch], 0));
+          if (int rc = launch_dune(p, d, s, dune_cta_limit)) return rc;
+        }
       }
       nb::NrmpParams n{};
       n.nom_s = out_s + (size_t)lo * 3 * T1s; n.nom_u = out_u + (size_t)lo * 2 * T; n.ref_s = ref_s + (size_t)lo * 3 * T1s; n.ref_us = ref_us + (size_t)lo * T;
@@ -654,6 +709,7 @@ int nb_pan_forward(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const 
   NB_CUDA(cudaGetLastError());
   return NB_OK;
 }
+}  // namespace
 
 namespace {
 __global__ void adj_load_kernel(int n_s, int n_u, int n_d, int n_t, const float* gs, const float* gu, const float* gd, double* ds, double* du, double* dd,
@@ -742,6 +798,70 @@ int nb_pan_read_diagnostics(nb_pan_t* p, int32_t B, int32_t* ipm_iterations, voi
   return NB_OK;
 }
 
+namespace {
+// Upload of the host inputs into the handle's staging buffer on the copy stream, in env chunks, and the forward pass on `st` that
+// consumes them chunk by chunk; outputs go to the device pointers given.  Nothing is synchronised here.
+int pan_forward_from_host(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const float* nom_u, const float* ref_s, const float* ref_us,
+                          const float* points, const float* velocities, const int32_t* num_points, float* out_s, float* out_u, float* out_d,
+                          float* out_min_distance, int32_t* out_iters, int32_t* out_status, cudaStream_t st) {
+  const size_t T = p->cfg.receding, T1 = T + 1;
+  const size_t n_s = (size_t)B * 3 * T1, n_u = (size_t)B * 2 * T, n_r = (size_t)B * T, n_p = (size_t)B * 2 * N;
+  const size_t in_floats = 2 * n_s + n_u + n_r + 2 * n_p;
+  if (!p->copy_stream) NB_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+  if (!p->ev_inputs_free) NB_CUDA(cudaEventCreateWithFlags(&p->ev_inputs_free, cudaEventDisableTiming));
+  for (int i = 0; i < nb_pan::kMaxChunks; ++i)
+    if (!p->ev_chunk[i]) NB_CUDA(cudaEventCreateWithFlags(&p->ev_chunk[i], cudaEventDisableTiming));
+  // whatever `st` still does with the staging buffer (the previous call) must be over before it is overwritten
+  NB_CUDA(cudaEventRecord(p->ev_inputs_free, st));
+  NB_CUDA(cudaStreamWaitEvent(p->copy_stream, p->ev_inputs_free, 0));
+  if (in_floats > p->h_in_floats) {
+    NB_CUDA(cudaStreamSynchronize(p->copy_stream));
+    if (p->h_in) cudaFree(p->h_in);
+    p->h_in = nullptr; p->h_in_floats = 0;
+    NB_CUDA(dalloc(&p->h_in, in_floats));
+    p->h_in_floats = in_floats;
+  }
+  if (!p->h_np) NB_CUDA(dalloc(&p->h_np, (size_t)p->cfg.max_envs));
+  float* d = p->h_in;
+  float* d_nom_s = d; d += n_s;
+  float* d_ref_s = d; d += n_s;
+  float* d_nom_u = d; d += n_u;
+  float* d_ref_us = d; d += n_r;
+  float* d_pts = d; d += n_p;
+  float* d_vel = d;
+  cudaStream_t cs = p->copy_stream;
+  auto h2d = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cs); };
+  NB_CUDA(h2d(d_nom_s, nom_s, n_s * 4));
+  NB_CUDA(h2d(d_ref_s, ref_s, n_s * 4));
+  NB_CUDA(h2d(d_nom_u, nom_u, n_u * 4));
+  NB_CUDA(h2d(d_ref_us, ref_us, n_r * 4));
+  if (num_points) NB_CUDA(h2d(p->h_np, num_points, (size_t)B * 4));
+  const bool with_pts = points && N > 0;
+  ChunkPlan plan;
+  plan.n = (with_pts && B >= 64 * p->h2d_chunks) ? p->h2d_chunks : 1;
+  for (int c = 0; c <= plan.n; ++c) plan.bound[c] = (int)((long long)B * c / plan.n);
+  for (int c = 0; c < plan.n; ++c) {
+    const size_t lo = (size_t)plan.bound[c] * 2 * N, cnt = (size_t)(plan.bound[c + 1] - plan.bound[c]) * 2 * N;
+    if (with_pts && cnt) NB_CUDA(h2d(d_pts + lo, points + lo, cnt * 4));
+    if (with_pts && velocities && cnt) NB_CUDA(h2d(d_vel + lo, velocities + lo, cnt * 4));
+    plan.ev[c] = p->ev_chunk[c];
+    NB_CUDA(cudaEventRecord(plan.ev[c], cs));
+  }
+  return pan_forward_impl(p, B, N, d_nom_s, d_nom_u, d_ref_s, d_ref_us, with_pts ? d_pts : nullptr, (with_pts && velocities) ? d_vel : nullptr,
+                          num_points ? p->h_np : nullptr, out_s, out_u, out_d, out_min_distance, out_iters, out_status, st, &plan);
+}
+}  // namespace
+
+int nb_pan_forward_h2d(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const float* nom_u, const float* ref_s, const float* ref_us,
+                       const float* points, const float* velocities, const int32_t* num_points, float* out_s, float* out_u, float* out_d,
+                       float* out_min_distance, int32_t* out_iters, int32_t* out_status, void* stream) {
+  if (int rc = check_forward_args(p, B, N)) return rc;
+  if (!nom_s || !nom_u || !ref_s || !ref_us || !out_s || !out_u || !out_d) return fail(NB_ERR_INVALID, "null tensor argument");
+  NB_CUDA(cudaSetDevice(p->cfg.device));
+  return pan_forward_from_host(p, B, N, nom_s, nom_u, ref_s, ref_us, points, velocities, num_points, out_s, out_u, out_d, out_min_distance, out_iters,
+                               out_status, (cudaStream_t)stream);
+}
+
 int nb_pan_forward_host(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, const float* nom_u, const float* ref_s,
                         const float* ref_us, const float* points, const float* velocities, const int32_t* num_points, float* out_s,
                         float* out_u, float* out_d, float* out_min_distance, int32_t* out_iters, int32_t* out_status, void* stream) {
@@ -750,46 +870,22 @@ int nb_pan_forward_host(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, c
   NB_CUDA(cudaSetDevice(p->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t T = p->cfg.receding, T1 = T + 1;
-  const size_t n_s = (size_t)B * 3 * T1, n_u = (size_t)B * 2 * T, n_r = (size_t)B * T, n_p = (size_t)B * 2 * N;
-  const size_t in_floats = 2 * n_s + n_u + n_r + 2 * n_p;
+  const size_t n_s = (size_t)B * 3 * T1, n_u = (size_t)B * 2 * T, n_r = (size_t)B * T;
   const size_t out_floats = n_s + n_u + n_r + (size_t)B;
-  if (in_floats > p->h_in_floats) {
-    if (p->h_in) cudaFree(p->h_in);
-    p->h_in = nullptr; p->h_in_floats = 0;
-    NB_CUDA(dalloc(&p->h_in, in_floats));
-    p->h_in_floats = in_floats;
-  }
   if (out_floats > p->h_out_floats) {
     if (p->h_out) cudaFree(p->h_out);
     p->h_out = nullptr; p->h_out_floats = 0;
     NB_CUDA(dalloc(&p->h_out, out_floats));
     p->h_out_floats = out_floats;
   }
-  if (!p->h_np) NB_CUDA(dalloc(&p->h_np, (size_t)p->cfg.max_envs));
   if (!p->h_io) NB_CUDA(dalloc(&p->h_io, 2 * (size_t)p->cfg.max_envs));
-  float* d = p->h_in;
-  float* d_nom_s = d; d += n_s;
-  float* d_ref_s = d; d += n_s;
-  float* d_nom_u = d; d += n_u;
-  float* d_ref_us = d; d += n_r;
-  float* d_pts = d; d += n_p;
-  float* d_vel = d;
-  auto h2d = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st); };
-  NB_CUDA(h2d(d_nom_s, nom_s, n_s * 4));
-  NB_CUDA(h2d(d_ref_s, ref_s, n_s * 4));
-  NB_CUDA(h2d(d_nom_u, nom_u, n_u * 4));
-  NB_CUDA(h2d(d_ref_us, ref_us, n_r * 4));
-  if (points && N > 0) NB_CUDA(h2d(d_pts, points, n_p * 4));
-  if (velocities && N > 0) NB_CUDA(h2d(d_vel, velocities, n_p * 4));
-  if (num_points) NB_CUDA(h2d(p->h_np, num_points, (size_t)B * 4));
   float* o = p->h_out;
   float* o_s = o; o += n_s;
   float* o_u = o; o += n_u;
   float* o_d = o; o += n_r;
   float* o_md = o;
-  int rc = nb_pan_forward(p, B, N, d_nom_s, d_nom_u, d_ref_s, d_ref_us, (points && N > 0) ? d_pts : nullptr,
-                          (velocities && N > 0) ? d_vel : nullptr, num_points ? p->h_np : nullptr, o_s, o_u, o_d, o_md, p->h_io,
-                          p->h_io + p->cfg.max_envs, st);
+  int rc = pan_forward_from_host(p, B, N, nom_s, nom_u, ref_s, ref_us, points, velocities, num_points, o_s, o_u, o_d, o_md, p->h_io,
+                                 p->h_io + p->cfg.max_envs, st);
   if (rc) return rc;
   auto d2h = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st); };
   NB_CUDA(d2h(out_s, o_s, n_s * 4));

@@ -69,11 +69,10 @@ class ShardedPAN:
     def step(self, nom_s, nom_u, ref_s, ref_us, points=None, velocities=None, num_points=None) -> torch.Tensor:
         pan = self.pan
         host = nom_s.device.type != "cuda"
-        if host:
-            up = lambda t: None if t is None else t.to(pan.device, non_blocking=True)
-            nom_s, nom_u, ref_s, ref_us, points, velocities, num_points = (up(t) for t in (nom_s, nom_u, ref_s, ref_us, points, velocities, num_points))
         with torch.no_grad():  # sharded control is inference (the gather is not differentiable); tune parameters through PAN itself
-            S, U, D = pan(nom_s, nom_u, ref_s, ref_us, points, velocities, num_points)
+            # host inputs: nb_pan_forward_h2d uploads them in env chunks on a copy stream, the first DUNE pass of a chunk starts when its
+            # points have landed; the results stay on the device for the gather
+            S, U, D = pan(nom_s, nom_u, ref_s, ref_us, points, velocities, num_points, device_out=host)
         B = S.shape[0]
         md = pan.min_distance if torch.is_tensor(pan.min_distance) else torch.full((B,), float("inf"), device=S.device)
         if D is None:

@@ -203,6 +203,29 @@ def test_stop_criterion_as_its_own_kernel_equals_the_fused_one():
     assert i0.min() < 6  # the criterion did fire
 
 
+def test_host_inputs_with_chunked_upload_equal_device_inputs():
+    """nb_pan_forward_h2d / nb_pan_forward_host upload the batch in environment chunks on a copy stream and run the first DUNE pass chunk
+    by chunk (batches of >= 64 environments per chunk): same bits as the device-resident call, ragged counts included."""
+    cfg = CONFIGS["C2"]
+    B = 300
+    inp = make_inputs(cfg, B=B, scene="obstacles")
+    counts = torch.from_numpy((np.arange(B) * 7 % (cfg.N + 1)).astype(np.int32))
+    t = to_cuda(inp)
+    pan = make_pan(cfg, K=3, max_envs=B)
+    with torch.no_grad():
+        ref = pan(t["nom_s"], t["nom_u"], t["ref_s"], t["ref_us"], t["points"], t["velocities"], num_points=counts.cuda())
+        ref = [x.cpu().numpy() for x in ref] + [pan.min_distance.cpu().numpy()]
+        pin = {k: (None if v is None else torch.from_numpy(np.ascontiguousarray(v)).pin_memory()) for k, v in inp.items()}
+        for mode in ("h2d", "host"):
+            out = pan(pin["nom_s"], pin["nom_u"], pin["ref_s"], pin["ref_us"], pin["points"], pin["velocities"], num_points=counts.pin_memory(),
+                      device_out=mode == "h2d")
+            assert out[0].is_cuda == (mode == "h2d")
+            torch.cuda.synchronize()
+            got = [x.cpu().numpy() for x in out] + [pan.min_distance.cpu().numpy()]
+            for x, y in zip(ref, got):
+                assert np.array_equal(x, y), mode
+
+
 def test_nrmp_warm_start_reaches_the_cold_start_optimum():
     """NB_OPT_NRMP_WARM: iteration 2's solve starts from iteration 1's solution; same optimum to the solver tolerance, fewer
     interior point iterations.  (K = 2: the first solve is cold in both runs, so the inputs of the second are bit-identical.)"""
