@@ -121,8 +121,8 @@ int nb_pan_set_adjust(nb_pan_t* pan, const float q_s[3], float p_u, float eta, f
 /* iter_num / iter_threshold are plain attributes in the reference (pan.py:63-64). */
 int nb_pan_set_iteration(nb_pan_t* pan, int32_t iter_num, float iter_threshold);
 
-/* Implementation switches (no reference counterpart).  NB_OPT_DUNE_KERNEL: 2 (default) = tcgen05 DUNE kernel
- * (UMMA with TMEM accumulators, fp16 hi/lo split, fp32 accumulate); 1 = the same arithmetic on warp-level mma.sync;
+/* Implementation switches (no reference counterpart).  NB_OPT_DUNE_KERNEL: 2 (the handle's initial value; the Python mirror selects 4) =
+ * tcgen05 DUNE kernel (UMMA with TMEM accumulators, fp16 hi/lo split, fp32 accumulate); 1 = the same arithmetic on warp-level mma.sync;
  * 0 = all-FP32 FFMA kernel, kept as the in-tree numerical reference of the same contract (needs the edge count
  * compiled in).
  * NB_OPT_OVERLAP: 1..4 = number of environment sub-batches pipelined on internal streams so that the DUNE kernel
