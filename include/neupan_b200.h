@@ -125,8 +125,10 @@ int nb_pan_set_iteration(nb_pan_t* pan, int32_t iter_num, float iter_threshold);
  * tcgen05 DUNE kernel (UMMA with TMEM accumulators, fp16 hi/lo split, fp32 accumulate); 1 = the same arithmetic on warp-level mma.sync;
  * 0 = all-FP32 FFMA kernel, kept as the in-tree numerical reference of the same contract (needs the edge count
  * compiled in).
- * NB_OPT_OVERLAP: 1..4 = number of environment sub-batches pipelined on internal streams so that the DUNE kernel
- * of one sub-batch shares the SMs with the NRMP kernel of another (results are identical; envs are independent).
+ * NB_OPT_OVERLAP: 1..4 = number of environment sub-batches pipelined on internal streams so that the DUNE kernels
+ * of one sub-batch share the SMs with the NRMP kernel of another (results are identical; envs are independent; batches with
+ * fewer than 64 environments per part are not split).  The handle starts with 2: the straggler tail of one half's NRMP launch
+ * and the small kernels between the big ones run under the other half's DUNE pass (C4: 20.6 -> 19.3 ms per step; 3 and 4 lose again).
  * NB_OPT_NRMP_WARM: 1 = inside one nb_pan_forward the NRMP solve of PAN iteration k > 0 starts from the solution of
  * iteration k-1 of the same environment (fewer interior point iterations on average, same optimum to the solver tolerance;
  * a warm start that is not converging by its 12th iteration is abandoned for a cold one); 0 (default) = every solve starts

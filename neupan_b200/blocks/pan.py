@@ -100,7 +100,9 @@ class PAN(torch.nn.Module):
             dev = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
         self.device = torch.device("cuda", dev.index if dev.index is not None else 0)
         self._handle = None
-        self.overlap = int(kwargs.get("overlap", 1))  # env sub-batches pipelined on internal streams (1 = off)
+        # env sub-batches pipelined on internal streams (1 = off; batches below 64 per part are never split): the stragglers of one half's NRMP
+        # launch and the small kernels between the big ones run under the other half's DUNE pass -- 20.6 -> 19.3 ms per C4 step at 2, 3 and 4 lose again
+        self.overlap = int(kwargs.get("overlap", 2))
         self.nrmp_warm = int(kwargs.get("nrmp_warm", 0))  # 1 = NRMP solves of PAN iterations k > 0 start from iteration k-1's solution (fewer IPM iterations on average, but stragglers: DESIGN.md 3.2)
         # 4 = tcgen05 with screening (default: bit-identical to 2, ~15 % less DUNE time), 2 = tcgen05 on every point, 3 = two threads per
         # point (experiment), 1 = mma.sync, 0 = all-FP32 FFMA

@@ -151,7 +151,12 @@ int launch_dune_tc(const DuneParams& prm_in, const unsigned char* d_image, const
         if (per_m < 1) per_m = 1;
       }
       if (e == cudaSuccess) {
-        int grid = sm_count * per_m;
+        static int cap = -1;  // NB_SCREEN_CTA_CAP (developer switch): fewer CTAs per SM, to leave room for a kernel of another stream (NB_OPT_OVERLAP)
+        if (cap < 0) {
+          const char* v = getenv("NB_SCREEN_CTA_CAP");
+          cap = v ? atoi(v) : 0;
+        }
+        int grid = sm_count * ((cap > 0 && cap < per_m) ? cap : per_m);
         if (grid > items_) grid = items_;
         dune_screen_mma_kernel<0><<<grid, 128, smem_m, st>>>(prm, d_screen_image);
         e = cudaGetLastError();

@@ -232,6 +232,12 @@ int launch_nrmp(nb_pan* p, nb::NrmpParams prm, cudaStream_t st, int counter_slot
       // persistent warps: as many CTAs as are resident at once; they pull environments from a counter until the batch is done
       int per_sm = 0;
       NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+      static int cap = -1;  // NB_NRMP_CTA_CAP (developer switch): fewer resident CTAs per SM, to share the SMs with a kernel of another stream
+      if (cap < 0) {
+        const char* v = getenv("NB_NRMP_CTA_CAP");
+        cap = v ? atoi(v) : 0;
+      }
+      if (cap > 0 && cap < per_sm) per_sm = cap;
       const int resident = (per_sm > 0 ? per_sm : 1) * p->sm_count;
       if (grid > resident) {
         grid = resident;
@@ -441,6 +447,10 @@ int nb_pan_create(const nb_pan_config* cfg, const float* weights, int64_t n_weig
   NB_CUDA(cudaMemset(p->prev_valid, 0, B * sizeof(int32_t)));
   NB_CUDA(cudaMemset(p->prev_count, 0, B * sizeof(int32_t)));
   NB_CUDA(cudaMemset(p->sel_count, 0, B * sizeof(int32_t)));
+  if (int rc = nb_pan_set_option(p, NB_OPT_OVERLAP, 2)) {  // the default: two sub-batches on internal streams (streams / events are made here)
+    nb_pan_destroy(p);
+    return rc;
+  }
   *out = p;
   return NB_OK;
 }
@@ -660,8 +670,9 @@ int pan_forward_impl(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, cons
             if (int rc = launch_dune(p, dc, s, dune_cta_limit)) return rc;
           }
         } else {
-          if (k == 0 && plan)
-            for (int ch = 1; ch < plan->n; ++ch) NB_CUDA(cudaStreamWaitEvent(s, plan->ev[ch], 0));
+          if (k == 0 && plan)  // a sub-batch on its own stream: the chunks that cover its environments
+            for (int ch = 1; ch < plan->n; ++ch)
+              if (plan->bound[ch] < hi && plan->bound[ch + 1] > lo) NB_CUDA(cudaStreamWaitEvent(s, plan->ev[ch], 0));
           if (int rc = launch_dune(p, d, s, dune_cta_limit)) return rc;
         }
       }
@@ -839,6 +850,7 @@ int pan_forward_from_host(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s,
   const bool with_pts = points && N > 0;
   ChunkPlan plan;
   plan.n = (with_pts && B >= 64 * p->h2d_chunks) ? p->h2d_chunks : 1;
+  if (with_pts && p->overlap > 1 && B >= 64 * p->overlap) plan.n = p->overlap;  // one chunk per sub-batch stream (the same env boundaries)
   for (int c = 0; c <= plan.n; ++c) plan.bound[c] = (int)((long long)B * c / plan.n);
   for (int c = 0; c < plan.n; ++c) {
     const size_t lo = (size_t)plan.bound[c] * 2 * N, cnt = (size_t)(plan.bound[c + 1] - plan.bound[c]) * 2 * N;

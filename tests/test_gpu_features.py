@@ -203,6 +203,27 @@ def test_stop_criterion_as_its_own_kernel_equals_the_fused_one():
     assert i0.min() < 6  # the criterion did fire
 
 
+@pytest.mark.parametrize("cname", ["C4", "C5"])
+def test_sub_batches_on_internal_streams_equal_one_stream(cname):
+    """NB_OPT_OVERLAP (default 2): the batch runs as sub-batches on internal streams -- environments are independent, so trajectories,
+    iteration counts and selections equal the single-stream run bit for bit, with the stop criterion switching environments off."""
+    cfg = CONFIGS[cname]
+    B = 300
+    inp = make_inputs(cfg, B=B, scene="obstacles")
+    outs = []
+    for ov in (1, 2, 4):
+        pan = make_pan(cfg, K=4, iter_threshold=0.1, max_envs=B, overlap=ov)
+        a = run_pan(pan, inp)
+        sel = {k: v.cpu().numpy() for k, v in pan.read_selection().items()}
+        outs.append((a, pan.iterations.cpu().numpy().copy(), sel))
+    for a, it, sel in outs[1:]:
+        for x, y in zip(outs[0][0], a):
+            assert np.array_equal(x, y)
+        assert np.array_equal(outs[0][1], it)
+        for k in ("mu", "lam", "points", "distance", "count"):
+            assert np.array_equal(outs[0][2][k], sel[k]), k
+
+
 def test_host_inputs_with_chunked_upload_equal_device_inputs():
     """nb_pan_forward_h2d / nb_pan_forward_host upload the batch in environment chunks on a copy stream and run the first DUNE pass chunk
     by chunk (batches of >= 64 environments per chunk): same bits as the device-resident call, ragged counts included."""
