@@ -649,30 +649,29 @@ int pan_forward_impl(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s, cons
         d.flag_list = p->flag_list + (size_t)lo * T1s; d.flag_count = p->flag_count + 4 * counter_slot; d.refine_list = p->refine_list + (size_t)2 * lo * T1s;
         d.screen_mma = p->screen_mma;
         d.skip_t0 = (k > 0 && p->dune_skip_t0) ? 1 : 0;  // the step-0 items of iteration 0 stand (DuneParams::skip_t0)
-        if (k == 0 && plan && plan->n > 1 && lo == 0 && hi == B) {
-          // the first DUNE pass chunk by chunk, each as soon as its points have landed: the upload of chunk c+1 overlaps the work on chunk c
+        if (k == 0 && plan && plan->n > 1) {
+          // the first DUNE pass of this range chunk by chunk, each as soon as its points have landed: the upload of chunk c+1 overlaps the
+          // work on chunk c (d describes the environments [lo, hi); a chunk's part of them is [clo, chi))
           for (int ch = 0; ch < plan->n; ++ch) {
-            const int clo = plan->bound[ch], chi = plan->bound[ch + 1];
+            const int clo = plan->bound[ch] > lo ? plan->bound[ch] : lo, chi = plan->bound[ch + 1] < hi ? plan->bound[ch + 1] : hi;
             if (chi <= clo) continue;
+            const size_t off = (size_t)(clo - lo);
             NB_CUDA(cudaStreamWaitEvent(s, plan->ev[ch], 0));
             nb::DuneParams dc = d;
-            dc.nom_s = d.nom_s + (size_t)clo * 3 * T1s; dc.points = d.points + (size_t)clo * 2 * N;
-            dc.velocities = d.velocities ? d.velocities + (size_t)clo * 2 * N : nullptr;
-            dc.num_points = d.num_points ? d.num_points + clo : nullptr;
-            dc.active = d.active + clo;
-            dc.sel_mu = d.sel_mu + (size_t)clo * T1s * Ms * Es; dc.sel_lam = d.sel_lam + (size_t)clo * T1s * Ms * 2;
-            dc.sel_pts = d.sel_pts + (size_t)clo * T1s * Ms * 2; dc.sel_dist = d.sel_dist + (size_t)clo * T1s * Ms; dc.sel_count = d.sel_count + clo;
-            dc.min_dist = d.min_dist + clo;
+            dc.nom_s = d.nom_s + off * 3 * T1s; dc.points = d.points + off * 2 * N;
+            dc.velocities = d.velocities ? d.velocities + off * 2 * N : nullptr;
+            dc.num_points = d.num_points ? d.num_points + off : nullptr;
+            dc.active = d.active + off;
+            dc.sel_mu = d.sel_mu + off * T1s * Ms * Es; dc.sel_lam = d.sel_lam + off * T1s * Ms * 2;
+            dc.sel_pts = d.sel_pts + off * T1s * Ms * 2; dc.sel_dist = d.sel_dist + off * T1s * Ms; dc.sel_count = d.sel_count + off;
+            dc.min_dist = d.min_dist + off;
             dc.B = chi - clo;
-            dc.cand_idx = d.cand_idx + (size_t)clo * T1s * nb::kCandMax; dc.cand_dt = d.cand_dt + (size_t)clo * T1s * nb::kCandMax;
-            dc.cand_cnt = d.cand_cnt + (size_t)clo * T1s;
-            dc.flag_list = d.flag_list + (size_t)clo * T1s; dc.refine_list = d.refine_list + (size_t)2 * clo * T1s;
+            dc.cand_idx = d.cand_idx + off * T1s * nb::kCandMax; dc.cand_dt = d.cand_dt + off * T1s * nb::kCandMax;
+            dc.cand_cnt = d.cand_cnt + off * T1s;
+            dc.flag_list = d.flag_list + off * T1s; dc.refine_list = d.refine_list + (size_t)2 * off * T1s;
             if (int rc = launch_dune(p, dc, s, dune_cta_limit)) return rc;
           }
         } else {
-          if (k == 0 && plan)  // a sub-batch on its own stream: the chunks that cover its environments
-            for (int ch = 1; ch < plan->n; ++ch)
-              if (plan->bound[ch] < hi && plan->bound[ch + 1] > lo) NB_CUDA(cudaStreamWaitEvent(s, plan->ev[ch], 0));
           if (int rc = launch_dune(p, d, s, dune_cta_limit)) return rc;
         }
       }
@@ -850,7 +849,10 @@ int pan_forward_from_host(nb_pan_t* p, int32_t B, int32_t N, const float* nom_s,
   const bool with_pts = points && N > 0;
   ChunkPlan plan;
   plan.n = (with_pts && B >= 64 * p->h2d_chunks) ? p->h2d_chunks : 1;
-  if (with_pts && p->overlap > 1 && B >= 64 * p->overlap) plan.n = p->overlap;  // one chunk per sub-batch stream (the same env boundaries)
+  if (with_pts && p->overlap > 1 && B >= 64 * p->overlap) {  // sub-batches on internal streams: chunk boundaries that contain theirs
+    plan.n = p->overlap * (B >= 128 * p->overlap ? 2 : 1);
+    if (plan.n > nb_pan::kMaxChunks) plan.n = p->overlap;
+  }
   for (int c = 0; c <= plan.n; ++c) plan.bound[c] = (int)((long long)B * c / plan.n);
   for (int c = 0; c < plan.n; ++c) {
     const size_t lo = (size_t)plan.bound[c] * 2 * N, cnt = (size_t)(plan.bound[c + 1] - plan.bound[c]) * 2 * N;
