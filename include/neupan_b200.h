@@ -140,7 +140,7 @@ int nb_pan_set_iteration(nb_pan_t* pan, int32_t iter_num, float iter_threshold);
  * NB_OPT_DIFFERENTIABLE: 1 = every NRMP solve of nb_pan_forward also stores what nb_pan_backward needs (one extra factorisation
  * at the optimum + ~5 KB per environment and iteration); 0 (default) = inference only.
  * NB_OPT_DUNE_SCREEN_MMA (with NB_OPT_DUNE_KERNEL = 4): 1 (default) = the screening pass runs on warp-level mma.sync with the
- * activations in registers (csrc/dune_screen_mma_kernel.cuh; clouds of at most 512 points, larger ones take the tcgen05 pass), 0 = on
+ * activations in registers (csrc/dune_screen_mma_kernel.cuh; clouds of at most 1024 points, larger ones take the tcgen05 pass), 0 = on
  * tcgen05 (csrc/dune_screen_kernel.cuh).  Same candidate contract, same final results (the refine / exact kernels are tcgen05 either way).
  * NB_OPT_DUNE_SKIP_T0 (with NB_OPT_DUNE_KERNEL = 4): 1 (default) = PAN iterations k > 0 of one nb_pan_forward do not re-evaluate the
  * step-0 items: nom_s[:, 0] is the fixed initial state (robot.py:234), so their inputs and results are those of iteration 0, which

@@ -104,10 +104,10 @@ class PAN(torch.nn.Module):
         # launch and the small kernels between the big ones run under the other half's DUNE pass -- 20.6 -> 19.3 ms per C4 step at 2, 3 and 4 lose again
         self.overlap = int(kwargs.get("overlap", 2))
         self.nrmp_warm = int(kwargs.get("nrmp_warm", 0))  # 1 = NRMP solves of PAN iterations k > 0 start from iteration k-1's solution (fewer IPM iterations on average, but stragglers: DESIGN.md 3.2)
-        # 4 = tcgen05 with screening (default: bit-identical to 2, ~15 % less DUNE time), 2 = tcgen05 on every point, 3 = two threads per
+        # 4 = screening pipeline (default: interval pass + exact tcgen05 network on the candidates, bit-identical to 2, ~35 % less DUNE time), 2 = tcgen05 on every point, 3 = two threads per
         # point (experiment), 1 = mma.sync, 0 = all-FP32 FFMA
         self.dune_kernel = int(kwargs.get("dune_kernel", 4))
-        # with dune_kernel = 4: the screening pass on mma.sync (1, default; clouds of <= 512 points) or tcgen05 (0); PAN iterations k > 0
+        # with dune_kernel = 4: the screening pass on mma.sync (1, default; clouds of <= 1024 points) or tcgen05 (0); PAN iterations k > 0
         # keep the step-0 items of iteration 0 (1, default: nom_s[:, 0] is the fixed initial state) or re-evaluate them (0).  Same results.
         self.dune_screen_mma = int(kwargs.get("dune_screen_mma", 1))
         self.dune_skip_t0 = int(kwargs.get("dune_skip_t0", 1))

@@ -12,7 +12,7 @@
 // points (585 clk of the legacy tensor pipe per scheduler) against 792 clk of MUFU.TANH -- the exact path (3 passes, 204 HMMA)
 // is the one that needs tcgen05, and keeps it (dune_refine_kernel / dune_tcp_kernel).
 //
-// Mapping: CTA = 4 warps = one (environment, step) item at a time; pass p, warp w: points [128 p + 32 w, +32) as two m16 tiles.
+// Mapping (clouds of up to 1024 points; see the kP template parameter): CTA = 4 warps = one (environment, step) item at a time; pass p, warp w: points [128 p + 32 w, +32) as two m16 tiles.
 // Lane (g = lane >> 2, tq = lane & 3) holds rows g, g+8 (tile 0), g, g+8 (tile 1) -- "row slots" 0..3 = local points g + 8 r --
 // and columns 8 j + 2 tq, +1 (j = 0..3) of every 32-wide activation; it OWNS local point 8 tq + g (coordinates in, key out), so
 // the four row slots of a quad are exactly the points its four lanes own (one shuffle each way, no shared memory).
@@ -165,10 +165,11 @@ __host__ __device__ inline size_t dune_screen_mma_smem_bytes(int N, int M) {
 #ifndef NB_SMMA_BLOCKS
 #define NB_SMMA_BLOCKS 5  // CTAs per SM the register allocation is made for: 96 registers, 12 B of spills (4: 21.57, 5: 21.37, 6: 21.81 ms per C4 step)
 #endif
-// Requires N <= 512 (every thread keeps the bounds of its <= 4 points in registers); the launcher sends larger clouds to
-// dune_screen_kernel, whose shared-memory key arrays have no such limit.
-template <int kDummy>
-__global__ void __launch_bounds__(128, NB_SMMA_BLOCKS) dune_screen_mma_kernel(const DuneParams prm, const unsigned char* __restrict__ image) {
+// kP = the most 128-point passes an item can need: every thread keeps the bounds of its <= kP points in registers, with the point's
+// index in the low kIdxBits bits of the key.  kP = 4: N <= 512 (96 registers, 5 CTAs per SM); kP = 8: N <= 1024 (4 CTAs per SM).  The
+// launcher sends larger clouds to dune_screen_kernel, whose shared-memory key arrays have no such limit.
+template <int kP>
+__global__ void __launch_bounds__(128, kP <= 4 ? NB_SMMA_BLOCKS : 4) dune_screen_mma_kernel(const DuneParams prm, const unsigned char* __restrict__ image) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   using I = TcImage;
   uint4* wfrag = reinterpret_cast<uint4*>(smem_dyn);
@@ -215,6 +216,11 @@ __global__ void __launch_bounds__(128, NB_SMMA_BLOCKS) dune_screen_mma_kernel(co
   const float gx0 = e0 < E ? prm.geo.G[e0][0] : 0.f, gy0 = e0 < E ? prm.geo.G[e0][1] : 0.f, h0 = e0 < E ? prm.geo.h[e0] : 0.f;
   const float gx1 = e1 < E ? prm.geo.G[e1][0] : 0.f, gy1 = e1 < E ? prm.geo.G[e1][1] : 0.f, h1 = e1 < E ? prm.geo.h[e1] : 0.f;
   const int own0 = 32 * warp + 8 * tq + g;  // the lane's point in pass 0 (pass p: + 128 p)
+  constexpr int kIdxBits = kP <= 4 ? 9 : 10;
+  constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1u;
+  // smallest value above k whose low kIdxBits bits carry the point's index: keys become unique (a REDUX round removes exactly one entry);
+  // rounding an upper bound UP only widens the candidate set
+  auto unique_key = [&](uint32_t k, int idx) -> uint32_t { return ((min(k, 0xFFFFF000u) + (kIdxMask + 1u)) & ~kIdxMask) | (uint32_t)idx; };
 
   // The raw point data of an item are copied asynchronously (cp.async, each thread exactly the <= 4 entries it reads itself: no
   // barrier) -- for the NEXT item as soon as this thread has read its last point of the current one.
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(128, NB_SMMA_BLOCKS) dune_screen_mma_kernel(co
     const float* px = prm.points + (size_t)bb * 2 * N;
     const float* vx = prm.velocities ? prm.velocities + (size_t)bb * 2 * N : nullptr;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kP; ++j) {
       const int i = own0 + 128 * j;
       if (i < nn) {
         tc::cp_async4(raw + i, px + i);
@@ -276,8 +282,10 @@ __global__ void __launch_bounds__(128, NB_SMMA_BLOCKS) dune_screen_mma_kernel(co
     }
     tc::cp_async_wait_all();
     // the bounds of the thread's points: a shift register (newest first); the point's index rides in the low 9 bits of the key
-    uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu, k3 = 0xFFFFFFFFu;
-    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    uint32_t kk[kP];
+    float ll[kP], dd[kP];
+#pragma unroll
+    for (int j = 0; j < kP; ++j) { kk[j] = 0xFFFFFFFFu; ll[j] = 0.f; dd[j] = 0.f; }
 
 #pragma unroll 1
     for (int base = 32 * warp; base < n; base += 128) {  // this warp's 32-point tiles
@@ -340,21 +348,20 @@ __global__ void __launch_bounds__(128, NB_SMMA_BLOCKS) dune_screen_mma_kernel(co
       for (int e = 0; e < kMaxEdges; ++e)
         if (e < E) sa += fabsf(fmaf(prm.geo.G[e][1], y0, prm.geo.G[e][0] * x0) - prm.geo.h[e]);
       const float eps = fmaf(prm.c_mu, sa, 1e-4f);
-      k3 = k2; l3 = l2; d3 = d2;
-      k2 = k1; l2 = l1; d2 = d1;
-      k1 = k0; l1 = l0; d1 = d0;
-      k0 = i < n ? tc::unique_key(orderable(d + eps), i) : 0xFFFFFFFFu;
-      l0 = d - eps; d0 = d;
+#pragma unroll
+      for (int j = kP - 1; j > 0; --j) { kk[j] = kk[j - 1]; ll[j] = ll[j - 1]; dd[j] = dd[j - 1]; }
+      kk[0] = i < n ? unique_key(orderable(d + eps), i) : 0xFFFFFFFFu;
+      ll[0] = d - eps; dd[0] = d;
     }
     if (item + (int)gridDim.x < items) {  // this thread is done with `raw`: its part of the next item
       if (stage_points(item + (int)gridDim.x)) staged = item + (int)gridDim.x;
     }
     if (NB_WHATIF & 4) {
-      if (tid == 0) prm.cand_cnt[item] = (k0 ^ k1 ^ k2 ^ k3) == 12345u ? (int)(l0 + l1 + l2 + l3 + d0 + d1 + d2 + d3) : 0;
+      if (tid == 0) prm.cand_cnt[item] = (kk[0] ^ kk[kP - 1]) == 12345u ? (int)(ll[0] + ll[kP - 1] + dd[0] + dd[kP - 1]) : 0;
       continue;
     }
     if (n <= kCandMax) {  // calibration mode: all points (they belong to warp 0's only tile), with their screened distance
-      if (k0 != 0xFFFFFFFFu) { out_idx[k0 & 0x1FFu] = (int)(k0 & 0x1FFu); out_dt[k0 & 0x1FFu] = d0; }
+      if (kk[0] != 0xFFFFFFFFu) { out_idx[kk[0] & kIdxMask] = (int)(kk[0] & kIdxMask); out_dt[kk[0] & kIdxMask] = dd[0]; }
       if (tid == 0) { prm.cand_cnt[item] = n; tc::refine_append(prm, item, n); }
       continue;
     }
@@ -362,11 +369,16 @@ __global__ void __launch_bounds__(128, NB_SMMA_BLOCKS) dune_screen_mma_kernel(co
     // the minimum), then every warp merges the 4 M survivors the same way.  Two block barriers per item: the per-warp lists, and
     // the candidate list; the candidate counter alternates between two words so that resetting it needs no third one.
     {
-      uint32_t q0 = k0, q1 = k1, q2 = k2, q3 = k3;
+      uint32_t q[kP];
+#pragma unroll
+      for (int j = 0; j < kP; ++j) q[j] = kk[j];
       for (int m = 0; m < M; ++m) {
-        const uint32_t md = __reduce_min_sync(0xffffffffu, min(min(q0, q1), min(q2, q3)));
-        q0 = q0 == md ? 0xFFFFFFFFu : q0; q1 = q1 == md ? 0xFFFFFFFFu : q1;
-        q2 = q2 == md ? 0xFFFFFFFFu : q2; q3 = q3 == md ? 0xFFFFFFFFu : q3;
+        uint32_t mine = q[0];
+#pragma unroll
+        for (int j = 1; j < kP; ++j) mine = min(mine, q[j]);
+        const uint32_t md = __reduce_min_sync(0xffffffffu, mine);
+#pragma unroll
+        for (int j = 0; j < kP; ++j) q[j] = q[j] == md ? 0xFFFFFFFFu : q[j];
         if (lane == 0) c32[warp * M + m] = md;
       }
     }
@@ -387,10 +399,11 @@ __global__ void __launch_bounds__(128, NB_SMMA_BLOCKS) dune_screen_mma_kernel(co
     auto take = [&](uint32_t k, float lb, float dt) {
       if (k != 0xFFFFFFFFu && orderable(lb) <= tau) {
         const int pos = atomicAdd(&cnt_s[par], 1);
-        if (pos < kCandMax) { list_s[pos] = (int)(k & 0x1FFu); ldt_s[pos] = dt; }
+        if (pos < kCandMax) { list_s[pos] = (int)(k & kIdxMask); ldt_s[pos] = dt; }
       }
     };
-    take(k0, l0, d0); take(k1, l1, d1); take(k2, l2, d2); take(k3, l3, d3);
+#pragma unroll
+    for (int j = 0; j < kP; ++j) take(kk[j], ll[j], dd[j]);
     __syncthreads();
     const int nc = cnt_s[par];
     if (nc <= kCandMax) {

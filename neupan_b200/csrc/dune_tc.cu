@@ -140,27 +140,31 @@ int launch_dune_tc(const DuneParams& prm_in, const unsigned char* d_image, const
     const int screen_mma = prm.screen_mma;
     cudaError_t e = cudaMemsetAsync(prm.flag_count, 0, 3 * sizeof(int32_t), st);
     const size_t smem_m = dune_screen_mma_smem_bytes(prm.N, prm.M);
-    if (screen_mma && prm.N <= 512 && (long long)smem_m <= max_smem_optin) {  // larger clouds: the tcgen05 screen kernel (key arrays in shared memory)
+    if (screen_mma && prm.N <= 1024 && (long long)smem_m <= max_smem_optin) {  // larger clouds: the tcgen05 screen kernel (key arrays in shared memory)
       // no TMEM in this kernel: residency is whatever registers and shared memory admit
-      static int per_m = -1;
-      static size_t per_m_smem = 0;
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(dune_screen_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
-      if (e == cudaSuccess && (per_m < 0 || per_m_smem != smem_m)) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_m, dune_screen_mma_kernel<0>, 128, smem_m);
-        per_m_smem = smem_m;
-        if (per_m < 1) per_m = 1;
-      }
-      if (e == cudaSuccess) {
-        static int cap = -1;  // NB_SCREEN_CTA_CAP (developer switch): fewer CTAs per SM, to leave room for a kernel of another stream (NB_OPT_OVERLAP)
-        if (cap < 0) {
-          const char* v = getenv("NB_SCREEN_CTA_CAP");
-          cap = v ? atoi(v) : 0;
+      auto go = [&](auto kern, int& per_m, size_t& per_m_smem) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+        if (e == cudaSuccess && (per_m < 0 || per_m_smem != smem_m)) {
+          e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_m, kern, 128, smem_m);
+          per_m_smem = smem_m;
+          if (per_m < 1) per_m = 1;
         }
-        int grid = sm_count * ((cap > 0 && cap < per_m) ? cap : per_m);
-        if (grid > items_) grid = items_;
-        dune_screen_mma_kernel<0><<<grid, 128, smem_m, st>>>(prm, d_screen_image);
-        e = cudaGetLastError();
-      }
+        if (e == cudaSuccess) {
+          static int cap = -1;  // NB_SCREEN_CTA_CAP (developer switch): fewer CTAs per SM, to leave room for a kernel of another stream (NB_OPT_OVERLAP)
+          if (cap < 0) {
+            const char* v = getenv("NB_SCREEN_CTA_CAP");
+            cap = v ? atoi(v) : 0;
+          }
+          int grid = sm_count * ((cap > 0 && cap < per_m) ? cap : per_m);
+          if (grid > items_) grid = items_;
+          kern<<<grid, 128, smem_m, st>>>(prm, d_screen_image);
+          e = cudaGetLastError();
+        }
+      };
+      static int per4 = -1, per8 = -1;
+      static size_t smem4 = 0, smem8 = 0;
+      if (prm.N <= 512) go(dune_screen_mma_kernel<4>, per4, smem4);
+      else go(dune_screen_mma_kernel<8>, per8, smem8);
     } else {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(dune_screen_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
       if (e == cudaSuccess) {
