@@ -5,14 +5,16 @@
 // nrmp.py:243-259), but dune_tcp_kernel pays the full fp32-accurate network -- fp16 hi/lo split, 3 MMA passes, exp2 + rcp tanh:
 // 1,730 instructions per point -- for every point.  Here:
 //
-//  1. dune_screen_kernel   every point through a SINGLE-pass fp16 network (activations and weights rounded to fp16 once, fp32
-//     accumulation, tanh by MUFU.TANH f16x2: ~45 % of the instructions, 40 % of the MUFU work, a third of the MMAs), giving an
+//  1. screening pass       (dune_screen_mma_kernel.cuh for clouds of <= 1024 points -- the default --, dune_screen_kernel below
+//     otherwise or with NB_OPT_DUNE_SCREEN_MMA = 0): every point through a SINGLE-pass fp16 network (activations and weights rounded
+//     to fp16 once, fp32 accumulation, tanh by MUFU.TANH: ~45 % of the instructions, 40 % of the MUFU work, a third of the MMAs), giving an
 //     approximate distance d~ and a per-point error radius eps = c_mu sum_e |G_e p0 - h_e| + 1e-4 (d is linear in mu, |mu~ - mu|
 //     <= c_mu).  With tau = the M-th smallest upper bound d~ + eps, a point whose lower bound d~ - eps exceeds tau cannot be among
 //     the M smallest EXACT distances; the others (typically 11-16 of 500) are the item's candidates.
 //  2. dune_refine_kernel   the candidates through exactly the arithmetic of dune_tcp_kernel (same helpers, same MMA structure;
 //     rows of an MMA tile are independent, so a point's mu / distance are bit-identical to what the full kernel computes for it);
-//     one warp = one item's <= 32 candidates, 8 items per two-slot pass; per-warp REDUX selection, output rows.
+//     work lists by candidate count (filled by the screening kernels): an item with 17..32 candidates takes a warp, two items with
+//     <= 16 share one; 8 units per two-slot pass; rank-based selection inside the group, output rows.
 //  3. items with more than 32 candidates (or N <= 32: no screening needed) go to the exact path: dune_tcp_kernel with
 //     `only_flagged`.
 // Result: the same selection, mu, lam, distances as variant 2, bit for bit (tests compare the two on every config and on the full
