@@ -293,7 +293,7 @@ def test_capacity_growth_and_shape_checks():
     assert (pan.status.cpu().numpy() == 0).all()
 
 
-@pytest.mark.parametrize("dune_kernel", [2, 1, 0])
+@pytest.mark.parametrize("dune_kernel", [4, 2, 1, 0])
 def test_pentagon_robot_five_edges_random_weights(dune_kernel, tmp_path):
     """E = 5 (no shipped checkpoint has E != 4): a randomly initialised ObsPointNet(2, 5) saved in the
     reference's checkpoint format, run through both DUNE kernels and the oracle."""
